@@ -1,0 +1,77 @@
+"""Builds the in-tree native libraries.
+
+  navigation2_b200/libmppi_b200.so   the product: CUDA kernels + C ABI (include/mppi_b200.h), sm_100a only
+  oracle/_build/*.so, oracle/_ref/   the CPU oracle (test infrastructure) via oracle/Makefile
+
+`python -m navigation2_b200.build` builds both; `__graft_entry__.build()` calls build_all().
+nvcc cross-compiles sm_100a without a GPU; the resulting .so files travel to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "navigation2_b200", "csrc")
+LIB = os.path.join(ROOT, "navigation2_b200", "libmppi_b200.so")
+
+SOURCES = ["mppi_kernels.cu", "mppi_capi.cu", "mppi_config.cpp"]
+HEADERS = [
+    os.path.join(ROOT, "include", "mppi_b200.h"),
+    os.path.join(ROOT, "include", "mppi_math.h"),
+    os.path.join(CSRC, "mppi_device.h"),
+    os.path.join(CSRC, "mppi_kernels.h"),
+]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    # no FMA contraction on the device or the host side: bit-identical floats with the CPU oracle
+    # on everything that feeds a costmap index
+    "-fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall",
+    "-shared",
+]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: the product is CUDA-only, there is no CPU build")
+    return nvcc
+
+
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_product(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    if not force and not _stale(LIB, srcs + HEADERS + [os.path.abspath(__file__)]):
+        return LIB
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, *srcs, "-o", LIB]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return LIB
+
+
+def build_oracle(verbose: bool = False) -> None:
+    """Builds the checker (oracle/) and, when /root/reference exists, oracle/_ref from the reference's own header."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_product(force=force, verbose=verbose)
+    build_oracle(verbose=verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose=True)

@@ -1,0 +1,1390 @@
+// mppi_capi.cu — host runtime behind the C ABI of include/mppi_b200.h.
+//
+// Owns the device tensors, the streams and the pinned staging of one optimiser instance and runs
+// the host-side state machine of mppi::Optimizer (prepare / fallback / reset / speed limit,
+// src/optimizer.cpp) around the kernels of mppi_kernels.cu.  Everything numeric per trajectory
+// happens on the GPU; the host only prepares O(path length) scalars per cycle.
+// There is no CPU fallback: without a usable device every compute entry point fails.
+//
+// Reference citations are relative to /root/reference/nav2_mppi_controller/.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mppi_b200.h"
+#include "mppi_device.h"
+#include "mppi_kernels.h"
+#include "mppi_math.h"
+
+namespace
+{
+
+thread_local std::string g_create_error;
+
+struct HostRobot
+{
+  // Optimizer::last_command_vel_ (doubles of the float command)
+  double last_cmd_vx = 0, last_cmd_vy = 0, last_cmd_wz = 0;
+  // MotionModel::cmd_history_* ring buffers (motion_models.hpp:246-248), newest last
+  std::vector<float> hist_vx, hist_vy, hist_wz;
+  size_t fallback_counter = 0;  // optimizer.cpp:283 (function-static there; per robot here)
+  // costmap geometry of the last upload
+  bool map_valid = false;
+  uint32_t size_x = 0, size_y = 0, pitch = 0;
+  double resolution = 0, origin_x = 0, origin_y = 0;
+  std::vector<uint8_t> map_host;  // tight copy (path validity is evaluated on the host, O(n_path))
+  bool noise_injected = false;
+  uint32_t noise_epoch = 0;
+};
+
+#define CU_CHECK(h, call) \
+  do { \
+    cudaError_t e__ = (call); \
+    if (e__ != cudaSuccess) { \
+      (h)->error = std::string(#call) + ": " + cudaGetErrorString(e__); \
+      return MPPI_ERR_CUDA; \
+    } \
+  } while (0)
+
+}  // namespace
+
+struct MppiHandle
+{
+  MppiConfig cfg{};
+  std::string error;
+  int R = 1, B = 0, Bglobal = 0, T = 0;
+  bool holo = false;
+  bool shift = false;
+  float controller_period = 0.0f;
+  // settings_.base_constraints / constraints (speed limit), optimizer.cpp:115-123,152
+  float base_vx_max = 0, base_vx_min = 0, base_vy = 0, base_wz = 0;
+  float c_vx_max = 0, c_vx_min = 0, c_vy = 0, c_wz = 0;
+  float ax_max = 0, ax_min = 0, ay_max = 0, ay_min = 0, az_max = 0;
+  int off_vx = 0, off_vy = 0, off_wz = 0;
+  uint32_t validator_samples = 0;
+  int n_pa = 0, pa_step = 1, cc_ns = 0;
+  int critic_of_type[MPPI_CRITIC_TYPE_COUNT];
+  int path_angle_mode = 0;
+  std::vector<HostRobot> robots;
+  DevStatic h_static{};
+
+  cudaStream_t stream = nullptr, side = nullptr;
+  cudaEvent_t map_event = nullptr;
+  bool map_event_pending = false;
+
+  // device buffers
+  float * d_noise[3] = {nullptr, nullptr, nullptr};   // vx, vy, wz
+  float * d_cv[3] = {nullptr, nullptr, nullptr};
+  float * d_state[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // vx vy wz x y yaw
+  float * d_u = nullptr, * d_u_saved = nullptr;
+  float * d_hist = nullptr, * d_hist_saved = nullptr;
+  float * d_terms = nullptr, * d_obs_raw = nullptr, * d_obs_rep = nullptr, * d_last = nullptr;
+  float * d_pa = nullptr, * d_costs = nullptr, * d_softmax = nullptr, * d_critic_costs = nullptr;
+  uint8_t * d_collisions = nullptr;
+  uint32_t * d_dbg_cost = nullptr, * d_dbg_obs = nullptr;
+  int32_t * d_red = nullptr;
+  float * d_partials = nullptr, * d_slot = nullptr, * d_slot_all = nullptr;
+  uint8_t * d_map = nullptr;
+  size_t map_stride = 0;
+  DevStatic * d_static = nullptr;
+  uint8_t * d_cycle_block = nullptr, * d_cycle_saved = nullptr;   // [DevCycle R][path R*4*max_path f32][valid R*max_path]
+  uint8_t * d_out = nullptr;
+  size_t out_stride = 0;
+  int n_partial_blocks = 1;
+  int max_path = 0;
+  // pinned host staging
+  uint8_t * h_cycle_block = nullptr;
+  size_t cycle_block_bytes = 0;
+  uint8_t * h_out = nullptr;
+  uint8_t * h_map_stage = nullptr;
+  size_t map_stage_bytes = 0;
+
+  bool have_cycle = false;     // a cycle block is resident (mppi_enqueue_resident allowed)
+  bool from_tensors_loaded = false;
+  uint64_t launches = 0;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+  size_t timing_used = 0;
+
+  DevCycle * hcyc(int r) {return reinterpret_cast<DevCycle *>(h_cycle_block) + r;}
+  float * hpath(int r) {
+    return reinterpret_cast<float *>(h_cycle_block + sizeof(DevCycle) * R) + static_cast<size_t>(r) * 4 * max_path;
+  }
+  uint8_t * hvalid(int r) {
+    return h_cycle_block + sizeof(DevCycle) * R + sizeof(float) * 4 * max_path * R + static_cast<size_t>(r) * max_path;
+  }
+};
+
+namespace
+{
+
+void free_device(MppiHandle * h)
+{
+  auto F = [](auto *& p) {if (p) {cudaFree(p); p = nullptr;}};
+  for (auto & p : h->d_noise) {F(p);}
+  for (auto & p : h->d_cv) {F(p);}
+  for (auto & p : h->d_state) {F(p);}
+  F(h->d_u); F(h->d_u_saved); F(h->d_hist); F(h->d_hist_saved); F(h->d_terms); F(h->d_obs_raw);
+  F(h->d_obs_rep); F(h->d_last); F(h->d_pa); F(h->d_costs); F(h->d_softmax); F(h->d_critic_costs);
+  F(h->d_collisions); F(h->d_dbg_cost); F(h->d_dbg_obs); F(h->d_red); F(h->d_partials); F(h->d_slot);
+  F(h->d_slot_all); F(h->d_static); F(h->d_cycle_block); F(h->d_cycle_saved); F(h->d_out);
+  if (h->h_cycle_block) {cudaFreeHost(h->h_cycle_block); h->h_cycle_block = nullptr;}
+  if (h->h_out) {cudaFreeHost(h->h_out); h->h_out = nullptr;}
+}
+
+// MotionModel::offsetSteps (motion_models.hpp:221-227) and predict's own rounding (:160-162)
+int offset_steps(float delay, float model_dt)
+{
+  if (delay <= 0.0f || model_dt <= 0.0f) {return 0;}
+  return static_cast<int>(std::floor((delay / model_dt) + 0.5));
+}
+
+// InflationLayer::computeCost via the C ABI helper
+float find_circumscribed_cost(const MppiHandle * h, const HostRobot & rb, bool cost_critic)
+{
+  // cost_critic.cpp:85-129 / obstacles_critic.cpp:70-103
+  double result = -1.0;
+  const double circum_radius = h->cfg.circumscribed_radius;
+  if (static_cast<float>(circum_radius) == 0.0f) {
+    return 0.0f;  // circumscribed_radius_ starts at 0: early return of the cached 0
+  }
+  if (h->cfg.has_inflation_layer) {
+    if (cost_critic && h->cfg.inflation_radius < circum_radius) {
+      return 0.0f;
+    }
+    result = mppi_inflation_compute_cost(
+      circum_radius / rb.resolution, rb.resolution, h->cfg.inscribed_radius,
+      h->cfg.inflation_cost_scaling_factor);
+  }
+  return static_cast<float>(result);
+}
+
+int validate_and_derive(MppiHandle * h, const MppiConfig & c, std::string & err)
+{
+  if (c.abi_version != MPPI_ABI_VERSION) {err = "abi_version mismatch"; return MPPI_ERR_INVALID_ARGUMENT;}
+  if (c.n_robots < 1 || c.batch_size < 1 || c.time_steps < 2 || c.iteration_count < 1) {
+    err = "n_robots, batch_size, iteration_count must be >= 1 and time_steps >= 2";
+    return MPPI_ERR_INVALID_ARGUMENT;
+  }
+  if (c.n_critics > MPPI_MAX_CRITICS) {err = "too many critics"; return MPPI_ERR_INVALID_ARGUMENT;}
+  if (c.motion_model < 0 || c.motion_model > 2) {
+    err = "Failed to load motion model plugin";  // optimizer.cpp:683
+    return MPPI_ERR_CONFIG;
+  }
+  if (c.shard_world < 1 || c.shard_rank >= c.shard_world || c.batch_size % c.shard_world != 0) {
+    err = "batch_size must be divisible by shard_world and shard_rank < shard_world";
+    return MPPI_ERR_INVALID_ARGUMENT;
+  }
+  if (!(c.model_dt > 0.0f) || !(c.controller_frequency > 0.0) || !(c.temperature > 0.0f)) {
+    err = "model_dt, controller_frequency and temperature must be positive";
+    return MPPI_ERR_INVALID_ARGUMENT;
+  }
+  h->cfg = c;
+  h->R = static_cast<int>(c.n_robots);
+  h->Bglobal = static_cast<int>(c.batch_size);
+  h->B = static_cast<int>(c.batch_size / c.shard_world);
+  h->T = static_cast<int>(c.time_steps);
+  h->holo = c.motion_model == MPPI_MODEL_OMNI;
+  if (h->cfg.sgf_order < 1 || h->cfg.sgf_order > 2) {h->cfg.sgf_order = 2;}  // optimizer.cpp:130-133
+
+  // optimizer.cpp:135-148 sign fix-ups
+  h->ax_max = std::fabs(c.ax_max);
+  h->ax_min = c.ax_min > 0.0f ? -1.0f * c.ax_min : c.ax_min;
+  h->ay_max = c.ay_max;
+  h->ay_min = c.ay_min > 0.0f ? -1.0f * c.ay_min : c.ay_min;
+  h->az_max = c.az_max;
+  h->base_vx_max = c.vx_max; h->base_vx_min = c.vx_min; h->base_vy = c.vy_max; h->base_wz = c.wz_max;
+  h->c_vx_max = c.vx_max; h->c_vx_min = c.vx_min; h->c_vy = c.vy_max; h->c_wz = c.wz_max;
+
+  // optimizer.cpp:157-181 controller period / setOffset
+  h->controller_period = static_cast<float>(1.0 / c.controller_frequency);
+  {
+    constexpr double eps = 1e-6;
+    const double controller_period = h->controller_period;
+    h->shift = false;
+    if ((controller_period + eps) < c.model_dt) {
+      // "Controller period is less then model dt, consider setting it equal"
+    } else if (std::abs(controller_period - c.model_dt) < eps) {
+      h->shift = true;
+    } else {
+      err = "Controller period more then model dt, set it equal to model dt";
+      return MPPI_ERR_CONFIG;
+    }
+  }
+  h->off_vx = offset_steps(c.model_delay_vx, c.model_dt);
+  h->off_vy = offset_steps(c.model_delay_vy, c.model_dt);
+  h->off_wz = offset_steps(c.model_delay_wz, c.model_dt);
+  if (h->off_vx > MPPI_MAX_DELAY_STEPS || h->off_vy > MPPI_MAX_DELAY_STEPS || h->off_wz > MPPI_MAX_DELAY_STEPS) {
+    err = "model_delay_* exceeds MPPI_MAX_DELAY_STEPS model steps";
+    return MPPI_ERR_UNSUPPORTED;
+  }
+  // optimal_trajectory_validator.hpp:87-97
+  h->validator_samples = static_cast<uint32_t>(c.collision_lookahead_time / c.model_dt);
+  if (h->validator_samples > c.time_steps) {h->validator_samples = c.time_steps;}
+
+  // critics (critic_manager.cpp:44-69 + each initialize())
+  DevStatic & s = h->h_static;
+  std::memset(&s, 0, sizeof(s));
+  for (int i = 0; i < MPPI_CRITIC_TYPE_COUNT; ++i) {s.critic_of_type[i] = -1; h->critic_of_type[i] = -1;}
+  s.n_critics = static_cast<int32_t>(c.n_critics);
+  h->n_pa = 0; h->pa_step = 1; h->cc_ns = 0;
+  for (uint32_t k = 0; k < c.n_critics; ++k) {
+    const MppiCriticParams & p = c.critics[k];
+    if (p.type < 0 || p.type >= MPPI_CRITIC_TYPE_COUNT) {
+      err = "unknown critic type";  // pluginlib would fail to load the class
+      return MPPI_ERR_CONFIG;
+    }
+    if (s.critic_of_type[p.type] >= 0) {
+      err = "a critic type may be listed only once";
+      return MPPI_ERR_UNSUPPORTED;
+    }
+    s.critic_of_type[p.type] = static_cast<int32_t>(k);
+    h->critic_of_type[p.type] = static_cast<int>(k);
+    DevCritic & d = s.critics[k];
+    d.type = p.type;
+    d.enabled = p.enabled;
+    d.power = p.cost_power;
+    d.weight = p.type == MPPI_CRITIC_COST ? p.cost_weight / 254.0f : p.cost_weight;  // cost_critic.cpp:39
+    d.consider_footprint = p.consider_footprint;
+    d.critical_cost = p.critical_cost;
+    d.near_collision_cost = static_cast<float>(p.near_collision_cost);
+    d.collision_cost = p.collision_cost;
+    d.step = p.trajectory_point_step;
+    d.repulsion_weight = p.repulsion_weight;
+    d.critical_weight = p.critical_weight;
+    d.collision_margin_distance = p.collision_margin_distance;
+    d.symmetric_yaw_tolerance = p.symmetric_yaw_tolerance;
+    d.max_path_occupancy_ratio = p.max_path_occupancy_ratio;
+    d.offset_from_furthest = p.offset_from_furthest;
+    d.use_path_orientations = p.use_path_orientations;
+    d.max_angle_to_furthest = p.max_angle_to_furthest;
+    d.mode = p.mode;
+    d.deadband[0] = std::fabs(p.deadband_velocities[0]);
+    d.deadband[1] = std::fabs(p.deadband_velocities[1]);
+    d.deadband[2] = std::fabs(p.deadband_velocities[2]);
+    if (p.type == MPPI_CRITIC_COST || p.type == MPPI_CRITIC_OBSTACLES) {
+      // cost_critic.cpp:57-71, obstacles_critic.cpp:46-60
+      if ((c.use_radius != 0) == (p.consider_footprint != 0) && c.use_radius) {
+        err = "Considering footprint in collision checking but no robot footprint provided in the costmap";
+        return MPPI_ERR_CONFIG;
+      }
+      if (p.consider_footprint && c.n_footprint < 3) {
+        err = "consider_footprint needs a footprint polygon of at least 3 points";
+        return MPPI_ERR_CONFIG;
+      }
+    }
+    if ((p.type == MPPI_CRITIC_COST || p.type == MPPI_CRITIC_PATH_ALIGN) && p.trajectory_point_step < 1) {
+      err = "trajectory_point_step must be >= 1";
+      return MPPI_ERR_INVALID_ARGUMENT;
+    }
+    if (p.type == MPPI_CRITIC_COST) {
+      h->cc_ns = (h->T - 1) / static_cast<int>(p.trajectory_point_step) + 1;
+    }
+    if (p.type == MPPI_CRITIC_PATH_ALIGN) {
+      h->pa_step = static_cast<int>(p.trajectory_point_step);
+      h->n_pa = (h->T - 1) / h->pa_step + 1;
+    }
+    if (p.type == MPPI_CRITIC_PATH_ANGLE) {
+      // path_angle_critic.cpp:25-50
+      bool reversing_allowed = true;
+      if (std::fabs(c.vx_min) < 1e-6f) {reversing_allowed = false;}
+      int mode = p.mode;
+      if (!reversing_allowed && mode == 1) {mode = 0;}
+      d.mode = mode;
+    }
+  }
+  if (c.validator_enabled && c.validator_consider_footprint && c.n_footprint < 3) {
+    err = "validator consider_footprint needs a footprint polygon";
+    return MPPI_ERR_CONFIG;
+  }
+  if (c.n_footprint > MPPI_MAX_FOOTPRINT) {err = "footprint too large"; return MPPI_ERR_INVALID_ARGUMENT;}
+  s.n_footprint = static_cast<int32_t>(c.n_footprint);
+  for (uint32_t i = 0; i < c.n_footprint; ++i) {s.footprint_x[i] = c.footprint_x[i]; s.footprint_y[i] = c.footprint_y[i];}
+  s.track_unknown = c.track_unknown;
+  // ObstaclesCritic::distanceToObstacle (obstacles_critic.cpp:105-118) tabulated per uint8 cost.
+  // `log(cost.cost)` there is the C double log applied to a float.
+  {
+    // inflation_scale_factor_ / inflation_radius_ are only filled inside findCircumscribedCost when a
+    // layer exists and the circumscribed radius differs from the cached 0 (obstacles_critic.cpp:75-91)
+    const bool have = c.has_inflation_layer && static_cast<float>(c.circumscribed_radius) != 0.0f;
+    const float scale_factor = have ? static_cast<float>(c.inflation_cost_scaling_factor) : 0.0f;
+    const float min_radius = static_cast<float>(c.inscribed_radius);
+    s.obstacle_scale_factor = scale_factor;
+    s.obstacle_inflation_radius = have ? static_cast<float>(c.inflation_radius) : 0.0f;
+    for (int v = 0; v < 256; ++v) {
+      const float cost = static_cast<float>(v);
+      float dist_to_obj = (scale_factor * min_radius - log(cost) + log(253.0f)) / scale_factor;
+      s.obstacle_dist_lut[1][v] = dist_to_obj;
+      dist_to_obj -= min_radius;
+      s.obstacle_dist_lut[0][v] = dist_to_obj;
+    }
+  }
+  s.param_vx_max = c.vx_max; s.param_vx_min = c.vx_min; s.param_vy_max = c.vy_max;
+  s.min_turning_r = c.min_turning_r;
+  s.motion_model = c.motion_model;
+  s.max_delta_vx = c.model_dt * h->ax_max;
+  s.min_delta_vx = c.model_dt * h->ax_min;
+  s.max_delta_vy = c.model_dt * h->ay_max;
+  s.min_delta_vy = c.model_dt * h->ay_min;
+  s.max_delta_wz = c.model_dt * h->az_max;
+  s.offset_vx = h->off_vx; s.offset_vy = h->off_vy; s.offset_wz = h->off_wz;
+  s.clamp_raw_controls = c.clamp_raw_controls;
+  s.model_dt = c.model_dt;
+  s.controller_period = h->controller_period;
+  s.shift_control_sequence = h->shift ? 1 : 0;
+  s.gamma_vx = c.gamma / (c.vx_std * c.vx_std);
+  s.gamma_wz = c.gamma / (c.wz_std * c.wz_std);
+  s.gamma_vy = c.gamma / (c.vy_std * c.vy_std);
+  s.use_gamma_wz = c.wz_std > 0.0f ? 1 : 0;
+  s.inv_temp = 1.0f / c.temperature;
+  s.sgf_order = h->cfg.sgf_order;
+  s.ax_max = h->ax_max; s.ax_min = h->ax_min; s.ay_max = h->ay_max; s.ay_min = h->ay_min; s.az_max = h->az_max;
+  s.validator_enabled = c.validator_enabled;
+  s.validator_consider_footprint = c.validator_consider_footprint;
+  s.validator_samples = h->validator_samples;
+  return MPPI_OK;
+}
+
+int allocate(MppiHandle * h)
+{
+  free_device(h);
+  const size_t R = h->R, B = h->B, T = h->T;
+  const size_t bt = R * B * T;
+  const bool mat = h->cfg.materialize_tensors != 0;
+  const int n_critics = static_cast<int>(h->cfg.n_critics);
+  for (int i = 0; i < 3; ++i) {CU_CHECK(h, cudaMalloc(&h->d_noise[i], bt * sizeof(float)));}
+  CU_CHECK(h, cudaMemset(h->d_noise[1], 0, bt * sizeof(float)));
+  if (mat || h->cfg.clamp_raw_controls) {
+    for (int i = 0; i < 3; ++i) {
+      CU_CHECK(h, cudaMalloc(&h->d_cv[i], bt * sizeof(float)));
+      CU_CHECK(h, cudaMemset(h->d_cv[i], 0, bt * sizeof(float)));
+    }
+  }
+  if (mat) {
+    for (int i = 0; i < 6; ++i) {
+      CU_CHECK(h, cudaMalloc(&h->d_state[i], bt * sizeof(float)));
+      CU_CHECK(h, cudaMemset(h->d_state[i], 0, bt * sizeof(float)));
+    }
+  }
+  CU_CHECK(h, cudaMalloc(&h->d_u, R * 3 * T * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_u_saved, R * 3 * T * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_hist, R * 12 * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_hist_saved, R * 12 * sizeof(float)));
+  CU_CHECK(h, cudaMemset(h->d_u, 0, R * 3 * T * sizeof(float)));
+  CU_CHECK(h, cudaMemset(h->d_hist, 0, R * 12 * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_terms, R * (n_critics + 3) * B * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_obs_raw, R * B * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_obs_rep, R * B * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_last, R * 3 * B * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_pa, std::max<size_t>(1, R * 3 * h->n_pa * B) * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_costs, R * B * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_softmax, R * B * sizeof(float)));
+  CU_CHECK(h, cudaMemset(h->d_costs, 0, R * B * sizeof(float)));
+  CU_CHECK(h, cudaMemset(h->d_softmax, 0, R * B * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_collisions, R * B));
+  CU_CHECK(h, cudaMemset(h->d_collisions, 0, R * B));
+  if (h->cfg.visualize && n_critics > 0) {
+    CU_CHECK(h, cudaMalloc(&h->d_critic_costs, R * n_critics * B * sizeof(float)));
+    CU_CHECK(h, cudaMemset(h->d_critic_costs, 0, R * n_critics * B * sizeof(float)));
+  }
+  if (h->cfg.debug_cells) {
+    if (h->cc_ns > 0) {
+      CU_CHECK(h, cudaMalloc(&h->d_dbg_cost, R * h->cc_ns * B * sizeof(uint32_t)));
+      CU_CHECK(h, cudaMemset(h->d_dbg_cost, 0xFF, R * h->cc_ns * B * sizeof(uint32_t)));
+    }
+    if (h->critic_of_type[MPPI_CRITIC_OBSTACLES] >= 0) {
+      CU_CHECK(h, cudaMalloc(&h->d_dbg_obs, bt * sizeof(uint32_t)));
+      CU_CHECK(h, cudaMemset(h->d_dbg_obs, 0xFF, bt * sizeof(uint32_t)));
+    }
+  }
+  CU_CHECK(h, cudaMalloc(&h->d_red, R * RED_WORDS * sizeof(int32_t)));
+  {
+    std::vector<int32_t> init(R * RED_WORDS, 0);
+    for (size_t r = 0; r < R; ++r) {
+      init[r * RED_WORDS + RED_REP_MIN] = INT32_MIN;
+      init[r * RED_WORDS + RED_COST_MIN] = INT32_MIN;
+    }
+    CU_CHECK(h, cudaMemcpy(h->d_red, init.data(), init.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  h->n_partial_blocks = static_cast<int>(std::min<size_t>((B + MPPI_BLOCK_C - 1) / MPPI_BLOCK_C, MPPI_MAX_PARTIAL_BLOCKS));
+  if (R > 1) {
+    // fleet: keep the total grid near two waves of 148 SMs
+    const int per_robot = std::max<int>(1, static_cast<int>(MPPI_MAX_PARTIAL_BLOCKS / R));
+    h->n_partial_blocks = std::max(1, std::min(h->n_partial_blocks, per_robot));
+  }
+  CU_CHECK(h, cudaMalloc(&h->d_partials, R * h->n_partial_blocks * (1 + 3 * T) * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_slot, R * (2 + 3 * T) * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_slot_all, static_cast<size_t>(h->cfg.shard_world) * R * (2 + 3 * T) * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_static, sizeof(DevStatic)));
+  CU_CHECK(h, cudaMemcpy(h->d_static, &h->h_static, sizeof(DevStatic), cudaMemcpyHostToDevice));
+  h->max_path = 256;
+  h->out_stride = (sizeof(DevOutHeader) + 6 * T * sizeof(float) + 15) & ~static_cast<size_t>(15);
+  CU_CHECK(h, cudaMalloc(&h->d_out, R * h->out_stride));
+  CU_CHECK(h, cudaMemset(h->d_out, 0, R * h->out_stride));
+  CU_CHECK(h, cudaMallocHost(&h->h_out, R * h->out_stride));
+  return MPPI_OK;
+}
+
+int ensure_cycle_block(MppiHandle * h, int need_path)
+{
+  if (h->h_cycle_block && need_path <= h->max_path) {return MPPI_OK;}
+  int cap = h->max_path;
+  while (cap < need_path) {cap *= 2;}
+  if (cap > MPPI_MAX_PATH_POINTS) {
+    h->error = "path longer than MPPI_MAX_PATH_POINTS";
+    return MPPI_ERR_UNSUPPORTED;
+  }
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  if (h->h_cycle_block) {cudaFreeHost(h->h_cycle_block); h->h_cycle_block = nullptr;}
+  if (h->d_cycle_block) {cudaFree(h->d_cycle_block); h->d_cycle_block = nullptr;}
+  if (h->d_cycle_saved) {cudaFree(h->d_cycle_saved); h->d_cycle_saved = nullptr;}
+  h->max_path = cap;
+  h->cycle_block_bytes = sizeof(DevCycle) * h->R + sizeof(float) * 4 * cap * h->R + static_cast<size_t>(cap) * h->R;
+  h->cycle_block_bytes = (h->cycle_block_bytes + 15) & ~static_cast<size_t>(15);
+  CU_CHECK(h, cudaMallocHost(&h->h_cycle_block, h->cycle_block_bytes));
+  std::memset(h->h_cycle_block, 0, h->cycle_block_bytes);
+  CU_CHECK(h, cudaMalloc(&h->d_cycle_block, h->cycle_block_bytes));
+  CU_CHECK(h, cudaMalloc(&h->d_cycle_saved, h->cycle_block_bytes));
+  CU_CHECK(h, cudaMemset(h->d_cycle_block, 0, h->cycle_block_bytes));
+  h->have_cycle = false;
+  return MPPI_OK;
+}
+
+int generate_noise(MppiHandle * h, int robot)
+{
+  // one robot at a time: pointers offset to that robot's slab, R = 1, robot index in the counter
+  const size_t slab = static_cast<size_t>(h->B) * h->T;
+  HostRobot & rb = h->robots[robot];
+  // robot index and epoch are folded into the Philox key so each (robot, reset) draws a fresh tensor
+  const uint64_t seed = h->cfg.noise_seed ^ (static_cast<uint64_t>(robot) * 0x9E3779B97F4A7C15ull);
+  CU_CHECK(h, mppi_launch_philox(
+      h->d_noise[0] + robot * slab, h->d_noise[1] + robot * slab, h->d_noise[2] + robot * slab,
+      h->B, h->T, 1, static_cast<int>(h->cfg.shard_rank) * h->B, seed, rb.noise_epoch,
+      h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std, h->holo, h->stream));
+  rb.noise_epoch++;
+  rb.noise_injected = false;
+  h->launches++;
+  return MPPI_OK;
+}
+
+// Optimizer::reset (optimizer.cpp:183-211) for one robot
+int reset_robot(MppiHandle * h, int r, bool reset_dynamic_speed_limits)
+{
+  const size_t T = h->T;
+  CU_CHECK(h, cudaMemsetAsync(h->d_u + r * 3 * T, 0, 3 * T * sizeof(float), h->stream));
+  CU_CHECK(h, cudaMemsetAsync(h->d_hist + r * 12, 0, 12 * sizeof(float), h->stream));
+  CU_CHECK(h, cudaMemsetAsync(h->d_costs + static_cast<size_t>(r) * h->B, 0, h->B * sizeof(float), h->stream));
+  HostRobot & rb = h->robots[r];
+  rb.last_cmd_vx = rb.last_cmd_vy = rb.last_cmd_wz = 0.0;
+  if (reset_dynamic_speed_limits) {
+    h->c_vx_max = h->base_vx_max; h->c_vx_min = h->base_vx_min; h->c_vy = h->base_vy; h->c_wz = h->base_wz;
+  }
+  // motion_model_->setConstraints resizes, clearCommandHistory zeroes (motion_models.hpp:78-80,97-102)
+  rb.hist_vx.assign(h->off_vx, 0.0f);
+  rb.hist_vy.assign(h->off_vy, 0.0f);
+  rb.hist_wz.assign(h->off_wz, 0.0f);
+  // noise_generator_.reset (noise_generator.cpp:77-96): regenerate unless reference noise is injected
+  if (!rb.noise_injected) {
+    int rc = generate_noise(h, r);
+    if (rc != MPPI_OK) {return rc;}
+  }
+  return MPPI_OK;
+}
+
+void push_one(std::vector<float> & buf, float v)  // motion_models.hpp:232-237
+{
+  if (buf.empty()) {return;}
+  std::rotate(buf.begin(), buf.begin() + 1, buf.end());
+  buf.back() = v;
+}
+
+// Fill the per-robot cycle block: Optimizer::prepare (optimizer.cpp:300-343) plus the scalar
+// gates every critic's score() evaluates before touching tensors.
+int prepare_robot(MppiHandle * h, int r, const MppiCycleIn & in, int preset_furthest, bool from_tensors)
+{
+  HostRobot & rb = h->robots[r];
+  if (!rb.map_valid) {h->error = "no costmap uploaded for robot"; return MPPI_ERR_NOT_READY;}
+  if (in.n_path > 0 && (!in.path_x || !in.path_y || !in.path_yaw)) {
+    h->error = "path arrays are NULL";
+    return MPPI_ERR_INVALID_ARGUMENT;
+  }
+  DevCycle & cy = *h->hcyc(r);
+  std::memset(&cy, 0, sizeof(cy));
+  const MppiConfig & c = h->cfg;
+
+  // optimizer.cpp:307-330 latency-compensating speed prediction (double)
+  double sp_vx = in.speed_vx, sp_vy = in.speed_vy, sp_wz = in.speed_wz;
+  if (c.open_loop) {
+    sp_vx = rb.last_cmd_vx; sp_vy = rb.last_cmd_vy; sp_wz = rb.last_cmd_wz;
+  } else {
+    const double dt = h->controller_period;
+    sp_vx = std::clamp(rb.last_cmd_vx, in.speed_vx + dt * h->ax_min, in.speed_vx + dt * h->ax_max);
+    sp_wz = std::clamp(rb.last_cmd_wz, in.speed_wz - dt * h->az_max, in.speed_wz + dt * h->az_max);
+    if (h->holo) {
+      sp_vy = std::clamp(rb.last_cmd_vy, in.speed_vy + dt * h->ay_min, in.speed_vy + dt * h->ay_max);
+    }
+  }
+  cy.speed_vx = static_cast<float>(sp_vx);
+  cy.speed_vy = static_cast<float>(sp_vy);
+  cy.speed_wz = static_cast<float>(sp_wz);
+  cy.pose_x_d = in.pose_x; cy.pose_y_d = in.pose_y; cy.pose_yaw_d = in.pose_yaw;
+  cy.pose_x = static_cast<float>(in.pose_x);
+  cy.pose_y = static_cast<float>(in.pose_y);
+  cy.pose_yaw = static_cast<float>(in.pose_yaw);
+  mppi_sincosf(cy.pose_yaw, &cy.init_sin, &cy.init_cos);
+
+  // nav2_util/geometry_utils.hpp:155-165 calculate_path_length
+  double path_length = 0.0;
+  if (in.n_path >= 2) {
+    for (size_t i = 0; i + 1 < in.n_path; ++i) {
+      path_length += std::hypot(in.path_x[i] - in.path_x[i + 1], in.path_y[i] - in.path_y[i + 1]);
+    }
+  }
+  cy.local_path_length = static_cast<float>(path_length);
+  const int n = static_cast<int>(in.n_path);
+  cy.n_path = n;
+
+  // utils::toTensor (tools/utils.hpp:208-220) + integrated distances (utils.hpp:299-304)
+  float * px = h->hpath(r), * py = px + h->max_path, * pyaw = py + h->max_path, * pd = pyaw + h->max_path;
+  for (int i = 0; i < n; ++i) {
+    px[i] = static_cast<float>(in.path_x[i]);
+    py[i] = static_cast<float>(in.path_y[i]);
+    pyaw[i] = static_cast<float>(in.path_yaw[i]);
+  }
+  if (n > 0) {pd[0] = 0.0f;}
+  for (int i = 1; i < n; ++i) {
+    const float dx = px[i] - px[i - 1];
+    const float dy = py[i] - py[i - 1];
+    pd[i] = pd[i - 1] + sqrtf(dx * dx + dy * dy);
+  }
+
+  // costmap geometry (cost_critic.cpp:139-144 refreshes it every score())
+  cy.origin_x_d = rb.origin_x; cy.origin_y_d = rb.origin_y; cy.resolution_d = rb.resolution;
+  cy.origin_x_f = static_cast<float>(rb.origin_x);
+  cy.origin_y_f = static_cast<float>(rb.origin_y);
+  cy.resolution_f = static_cast<float>(rb.resolution);
+  cy.size_x = rb.size_x; cy.size_y = rb.size_y; cy.pitch = rb.pitch;
+
+  // utils::findPathCosts (tools/utils.hpp:358-387): validity of path points 0 .. n-2
+  uint8_t * valid = h->hvalid(r);
+  std::memset(valid, 0, h->max_path);
+  for (int i = 0; i + 1 < n; ++i) {
+    const double wx = px[i], wy = py[i];
+    bool ok = false;
+    if (!(wx < rb.origin_x || wy < rb.origin_y)) {
+      const unsigned int mx = static_cast<unsigned int>((wx - rb.origin_x) / rb.resolution);
+      const unsigned int my = static_cast<unsigned int>((wy - rb.origin_y) / rb.resolution);
+      if (mx < rb.size_x && my < rb.size_y) {
+        const uint8_t cost = rb.map_host[static_cast<size_t>(my) * rb.size_x + mx];
+        if (cost == 254 || cost == 253) {
+          ok = false;
+        } else if (cost == 255) {
+          ok = c.track_unknown != 0;
+        } else {
+          ok = true;
+        }
+      }
+    }
+    valid[i] = ok ? 1 : 0;
+  }
+
+  // critic gates (the scalar early-returns at the top of each score())
+  const float lpl = cy.local_path_length;
+  uint32_t active = 0, near_goal = 0;
+  bool need_furthest = false;
+  for (uint32_t k = 0; k < c.n_critics; ++k) {
+    const MppiCriticParams & p = c.critics[k];
+    bool on = p.enabled != 0;
+    switch (p.type) {
+      case MPPI_CRITIC_CONSTRAINT: break;
+      case MPPI_CRITIC_COST:
+      case MPPI_CRITIC_OBSTACLES:
+        if (lpl < p.near_goal_distance) {near_goal |= 1u << k;}
+        cy.possible_collision_cost[k] = find_circumscribed_cost(h, rb, p.type == MPPI_CRITIC_COST);
+        break;
+      case MPPI_CRITIC_GOAL:        // goal_critic.cpp:37-39
+      case MPPI_CRITIC_GOAL_ANGLE:  // goal_angle_critic.cpp:38-40
+        on = on && !(lpl > p.threshold_to_consider) && n > 0;
+        break;
+      case MPPI_CRITIC_PATH_ALIGN:  // path_align_critic.cpp:42-44
+      case MPPI_CRITIC_PATH_ANGLE:  // path_angle_critic.cpp:64-66
+        on = on && !(lpl < p.threshold_to_consider) && n > 0;
+        if (on) {need_furthest = true;}
+        break;
+      case MPPI_CRITIC_PATH_FOLLOW:  // path_follow_critic.cpp:40-42
+        on = on && !(n < 2 || lpl < p.threshold_to_consider);
+        if (on) {need_furthest = true;}
+        break;
+      case MPPI_CRITIC_PREFER_FORWARD:  // prefer_forward_critic.cpp:42-44
+        on = on && !(lpl < p.threshold_to_consider);
+        break;
+      case MPPI_CRITIC_TWIRLING:  // twirling_critic.cpp:39-48
+        if (in.has_goal_checker && lpl < in.goal_checker_xy_tolerance) {on = false;}
+        break;
+      case MPPI_CRITIC_VELOCITY_DEADBAND: break;
+      default: break;
+    }
+    if (on) {active |= 1u << k;}
+  }
+  cy.active_mask = active;
+  cy.near_goal_mask = near_goal;
+  cy.need_furthest = need_furthest ? 1 : 0;
+  cy.need_path_valid = 1;
+  if (n > 0) {
+    // utils::getLastPathPose (utils.hpp:227-245): float path point -> double Pose -> float in the critics
+    cy.goal_x = px[n - 1];
+    cy.goal_y = py[n - 1];
+    cy.goal_yaw = pyaw[n - 1];
+    cy.sym_goal_yaw = static_cast<float>(mppi_angles_normalize_angle(cy.goal_yaw + M_PI));  // goal_angle_critic.cpp:47
+  }
+  cy.c_vx_max = h->c_vx_max; cy.c_vx_min = h->c_vx_min; cy.c_vy = h->c_vy; cy.c_wz = h->c_wz;
+  for (size_t i = 0; i < rb.hist_vx.size(); ++i) {cy.hist_vx[i] = rb.hist_vx[i];}
+  for (size_t i = 0; i < rb.hist_vy.size(); ++i) {cy.hist_vy[i] = rb.hist_vy[i];}
+  for (size_t i = 0; i < rb.hist_wz.size(); ++i) {cy.hist_wz[i] = rb.hist_wz[i];}
+  cy.track_collisions = (c.visualize || from_tensors) ? 1 : 0;
+  cy.furthest_cached = preset_furthest >= 0 ? preset_furthest : -1;
+  cy.fail_flag = 0;
+  cy.run = 1;  // run
+
+  // costmap window staged in shared memory: the cells the trajectories can plausibly reach
+  {
+    const double reach_v = std::max({std::fabs(static_cast<double>(h->c_vx_max)),
+          std::fabs(static_cast<double>(h->c_vx_min)), h->holo ? static_cast<double>(h->c_vy) : 0.0});
+    const double reach = reach_v * h->T * c.model_dt * 1.25 + c.circumscribed_radius + 4.0 * rb.resolution;
+    int half = static_cast<int>(std::ceil(reach / rb.resolution));
+    half = std::min(std::max(half, 8), 96);
+    const int cx = static_cast<int>(std::floor((in.pose_x - rb.origin_x) / rb.resolution));
+    const int cyy = static_cast<int>(std::floor((in.pose_y - rb.origin_y) / rb.resolution));
+    int x0 = std::max(0, cx - half) & ~15;
+    int x1 = std::min(static_cast<int>(rb.pitch), ((cx + half + 1) + 15) & ~15);
+    int y0 = std::max(0, cyy - half);
+    int y1 = std::min(static_cast<int>(rb.size_y), cyy + half + 1);
+    if (x1 <= x0 || y1 <= y0 || x0 >= static_cast<int>(rb.pitch) || y0 >= static_cast<int>(rb.size_y)) {
+      x0 = 0; x1 = 0; y0 = 0; y1 = 0;  // robot far off the map: global lookups only
+    }
+    cy.win_x0 = x0; cy.win_y0 = y0; cy.win_w = x1 - x0; cy.win_h = y1 - y0;
+  }
+  return MPPI_OK;
+}
+
+KArgs make_args(MppiHandle * h)
+{
+  KArgs a{};
+  a.B = h->B; a.T = h->T; a.R = h->R;
+  a.b_offset = static_cast<int>(h->cfg.shard_rank) * h->B;
+  a.n_terms = static_cast<int>(h->cfg.n_critics) + 3;
+  a.n_pa = h->n_pa; a.pa_step = h->pa_step;
+  a.max_path = h->max_path;
+  a.world = static_cast<int>(h->cfg.shard_world); a.rank = static_cast<int>(h->cfg.shard_rank);
+  a.n_partial_blocks = h->n_partial_blocks;
+  a.materialize = h->cfg.materialize_tensors;
+  a.last_iteration = 0;
+  a.do_shift = h->shift ? 1 : 0;
+  a.noise_vx = h->d_noise[0]; a.noise_vy = h->d_noise[1]; a.noise_wz = h->d_noise[2];
+  a.cvx = h->d_cv[0]; a.cvy = h->d_cv[1]; a.cwz = h->d_cv[2];
+  a.vx = h->d_state[0]; a.vy = h->d_state[1]; a.wz = h->d_state[2];
+  a.x = h->d_state[3]; a.y = h->d_state[4]; a.yaw = h->d_state[5];
+  a.u = h->d_u; a.ctrl_hist = h->d_hist;
+  a.terms = h->d_terms; a.obs_raw = h->d_obs_raw; a.obs_rep = h->d_obs_rep; a.last_xyz = h->d_last;
+  a.pa_samples = h->d_pa; a.costs = h->d_costs; a.softmax = h->d_softmax;
+  a.critic_costs = h->d_critic_costs;
+  a.collisions = h->d_collisions;
+  a.dbg_cost_cells = h->d_dbg_cost; a.dbg_obstacle_cells = h->d_dbg_obs;
+  a.red = h->d_red; a.partials = h->d_partials;
+  a.ar2_slot = h->d_slot; a.ar2_all = h->d_slot_all;
+  a.costmap = h->d_map; a.map_stride = h->map_stride;
+  a.path = reinterpret_cast<const float *>(h->d_cycle_block + sizeof(DevCycle) * h->R);
+  a.path_valid = h->d_cycle_block + sizeof(DevCycle) * h->R + sizeof(float) * 4 * h->max_path * h->R;
+  a.cyc = reinterpret_cast<DevCycle *>(h->d_cycle_block);
+  a.st = h->d_static;
+  a.out = h->d_out; a.out_stride = h->out_stride;
+  return a;
+}
+
+struct LaunchPlan
+{
+  KSmemA sm_a;
+  int block_a;
+  int path_cap;
+};
+
+LaunchPlan make_plan(MppiHandle * h)
+{
+  LaunchPlan p{};
+  int max_n = 0, win_bytes = 0;
+  bool need = false;
+  for (int r = 0; r < h->R; ++r) {
+    const DevCycle & cy = *h->hcyc(r);
+    max_n = std::max(max_n, cy.n_path);
+    need = need || cy.need_furthest;
+    win_bytes = std::max(win_bytes, cy.win_w * cy.win_h);
+  }
+  p.path_cap = std::max(max_n, 1);
+  // small batches: narrower blocks spread the trajectories over more SMs (latency-bound regime)
+  p.block_a = (static_cast<size_t>(h->B) * h->R <= 148u * 64u) ? 64 : MPPI_BLOCK_A;
+  const int lag = std::max({std::max(h->off_vx, 1) - 1, std::max(h->off_wz, 1) - 1,
+        h->holo ? std::max(h->off_vy, 1) - 1 : 0});
+  const int ring = lag > 0 ? lag + 1 : 0;
+  const bool obstacles = h->critic_of_type[MPPI_CRITIC_OBSTACLES] >= 0;
+  p.sm_a = mppi_smem_layout_a(h->T, need ? p.path_cap : 0, obstacles, ring, p.block_a, win_bytes);
+  return p;
+}
+
+int enqueue_iterations(MppiHandle * h, cudaStream_t stream, const LaunchPlan & plan)
+{
+  KArgs a = make_args(h);
+  const int iters = static_cast<int>(h->cfg.iteration_count);
+  for (int it = 0; it < iters; ++it) {
+    a.last_iteration = (it == iters - 1) ? 1 : 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) {
+      if (h->timing_used == h->timing_events.size()) {
+        cudaEvent_t x, y;
+        CU_CHECK(h, cudaEventCreate(&x));
+        CU_CHECK(h, cudaEventCreate(&y));
+        h->timing_events.emplace_back(x, y);
+      }
+      e0 = h->timing_events[h->timing_used].first;
+      e1 = h->timing_events[h->timing_used].second;
+      h->timing_used++;
+      CU_CHECK(h, cudaEventRecord(e0, stream));
+    }
+    CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, h->holo, false, plan.block_a, stream));
+    if (h->timing) {CU_CHECK(h, cudaEventRecord(e1, stream));}
+    CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, false, plan.block_a, stream));
+    CU_CHECK(h, mppi_launch_softmax_partial(a, h->holo, stream));
+    CU_CHECK(h, mppi_launch_finalize(a, h->holo, 0, stream));
+    h->launches += 4;
+  }
+  return MPPI_OK;
+}
+
+int upload_cycle_block(MppiHandle * h, cudaStream_t stream)
+{
+  CU_CHECK(h, cudaMemcpyAsync(h->d_cycle_block, h->h_cycle_block, h->cycle_block_bytes, cudaMemcpyHostToDevice, stream));
+  return MPPI_OK;
+}
+
+int wait_map(MppiHandle * h, cudaStream_t stream)
+{
+  if (h->map_event_pending) {
+    CU_CHECK(h, cudaStreamWaitEvent(stream, h->map_event, 0));
+    h->map_event_pending = false;
+  }
+  return MPPI_OK;
+}
+
+// fallback() (optimizer.cpp:281-298) + the tail of evalControl (:261-269) for one robot after an
+// attempt.  Returns 1 if this robot must run another attempt.
+int finish_attempt(MppiHandle * h, int r, MppiCycleOut & out, bool & retry)
+{
+  const uint8_t * o = h->h_out + static_cast<size_t>(r) * h->out_stride;
+  const DevOutHeader * hdr = reinterpret_cast<const DevOutHeader *>(o);
+  HostRobot & rb = h->robots[r];
+  DevCycle & cy = *h->hcyc(r);
+  const int T = h->T;
+  out.fail_flag = hdr->fail_flag;
+  out.validation = hdr->validation;
+  out.furthest_reached_path_point = hdr->furthest;
+  const bool fail = hdr->fail_flag != 0 || hdr->validation != MPPI_VALIDATION_SUCCESS;
+  retry = false;
+  if (fail) {
+    int rc = reset_robot(h, r, false);
+    if (rc != MPPI_OK) {return rc;}
+    if (++rb.fallback_counter > h->cfg.retry_attempt_limit) {
+      rb.fallback_counter = 0;
+      out.status = MPPI_ERR_NO_VALID_CONTROL;  // "Optimizer fail to compute path"
+      cy.run = 0;
+      return MPPI_OK;
+    }
+    out.retries++;
+    // fail_flag and furthest_reached_path_point stay as they are: prepare() is not called again
+    cy.fail_flag = hdr->fail_flag;
+    cy.furthest_cached = hdr->furthest;
+    cy.run = 1;
+    retry = true;
+    return MPPI_OK;
+  }
+  rb.fallback_counter = 0;
+  cy.run = 0;
+  const float * u = reinterpret_cast<const float *>(o + sizeof(DevOutHeader));
+  const float * traj = u + 3 * T;
+  out.cmd_vx = hdr->cmd_vx;
+  out.cmd_vy = hdr->cmd_vy;
+  out.cmd_wz = hdr->cmd_wz;
+  // getControlFromSequenceAsTwist: pushCommandHistory + last_command_vel_ (optimizer.cpp:657, :263)
+  push_one(rb.hist_vx, hdr->cmd_vx);
+  push_one(rb.hist_vy, hdr->cmd_vy);
+  push_one(rb.hist_wz, hdr->cmd_wz);
+  rb.last_cmd_vx = hdr->cmd_vx;
+  rb.last_cmd_vy = h->holo ? hdr->cmd_vy : 0.0;
+  rb.last_cmd_wz = hdr->cmd_wz;
+  if (out.control_vx) {std::memcpy(out.control_vx, u, sizeof(float) * T);}
+  if (out.control_vy) {std::memcpy(out.control_vy, u + T, sizeof(float) * T);}
+  if (out.control_wz) {std::memcpy(out.control_wz, u + 2 * T, sizeof(float) * T);}
+  if (out.optimal_trajectory) {std::memcpy(out.optimal_trajectory, traj, sizeof(float) * 3 * T);}
+  out.status = MPPI_OK;
+  return MPPI_OK;
+}
+
+int check_handle(const MppiHandle * h)
+{
+  return h ? MPPI_OK : MPPI_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char * mppi_last_error(const MppiHandle * h)
+{
+  return h ? h->error.c_str() : g_create_error.c_str();
+}
+
+int mppi_create(const MppiConfig * cfg, MppiHandle ** out)
+{
+  if (!cfg || !out) {g_create_error = "null argument"; return MPPI_ERR_INVALID_ARGUMENT;}
+  *out = nullptr;
+  auto * h = new MppiHandle();
+  std::string err;
+  int rc = validate_and_derive(h, *cfg, err);
+  if (rc != MPPI_OK) {g_create_error = err; delete h; return rc;}
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+    delete h;
+    return MPPI_ERR_CUDA;
+  }
+  auto fail = [&](int code) {
+      g_create_error = h->error;
+      free_device(h);
+      if (h->stream) {cudaStreamDestroy(h->stream);}
+      if (h->side) {cudaStreamDestroy(h->side);}
+      if (h->map_event) {cudaEventDestroy(h->map_event);}
+      delete h;
+      return code;
+    };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+    cudaEventCreateWithFlags(&h->map_event, cudaEventDisableTiming) != cudaSuccess)
+  {
+    h->error = "stream/event creation failed";
+    return fail(MPPI_ERR_CUDA);
+  }
+  h->robots.assign(h->R, HostRobot());
+  rc = allocate(h);
+  if (rc != MPPI_OK) {return fail(rc);}
+  rc = ensure_cycle_block(h, 1);
+  if (rc != MPPI_OK) {return fail(rc);}
+  for (int r = 0; r < h->R; ++r) {
+    rc = reset_robot(h, r, true);
+    if (rc != MPPI_OK) {return fail(rc);}
+  }
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+    h->error = "device synchronisation failed after reset";
+    return fail(MPPI_ERR_CUDA);
+  }
+  *out = h;
+  return MPPI_OK;
+}
+
+int mppi_destroy(MppiHandle * h)
+{
+  if (!h) {return MPPI_OK;}
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->side);
+  free_device(h);
+  if (h->d_map) {cudaFree(h->d_map);}
+  if (h->h_map_stage) {cudaFreeHost(h->h_map_stage);}
+  for (auto & p : h->timing_events) {cudaEventDestroy(p.first); cudaEventDestroy(p.second);}
+  cudaEventDestroy(h->map_event);
+  cudaStreamDestroy(h->stream);
+  cudaStreamDestroy(h->side);
+  delete h;
+  return MPPI_OK;
+}
+
+int mppi_set_config(MppiHandle * h, const MppiConfig * cfg)
+{
+  if (!h || !cfg) {return MPPI_ERR_INVALID_ARGUMENT;}
+  if (cfg->n_robots != static_cast<uint32_t>(h->R)) {
+    h->error = "n_robots cannot change on a live handle";
+    return MPPI_ERR_INVALID_ARGUMENT;
+  }
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  const MppiConfig old = h->cfg;
+  std::string err;
+  int rc = validate_and_derive(h, *cfg, err);
+  if (rc != MPPI_OK) {
+    h->error = err;
+    std::string e2;
+    validate_and_derive(h, old, e2);
+    return rc;
+  }
+  for (auto & rb : h->robots) {
+    if (old.batch_size != cfg->batch_size || old.time_steps != cfg->time_steps || old.shard_world != cfg->shard_world) {
+      rb.noise_injected = false;  // shapes changed: injected tensors no longer fit
+    }
+  }
+  rc = allocate(h);
+  if (rc != MPPI_OK) {return rc;}
+  h->have_cycle = false;
+  // the ParametersHandler post-callback is Optimizer::reset() (optimizer.cpp:155)
+  for (int r = 0; r < h->R; ++r) {
+    if (h->robots[r].noise_injected) {h->robots[r].noise_injected = false;}
+    rc = reset_robot(h, r, true);
+    if (rc != MPPI_OK) {return rc;}
+  }
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+int mppi_reset(MppiHandle * h, uint32_t robot, int reset_dynamic_speed_limits)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  for (int r = 0; r < h->R; ++r) {
+    if (robot != UINT32_MAX && static_cast<int>(robot) != r) {continue;}
+    int rc = reset_robot(h, r, reset_dynamic_speed_limits != 0);
+    if (rc != MPPI_OK) {return rc;}
+  }
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+int mppi_set_speed_limit(MppiHandle * h, double speed_limit, int percentage)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  // optimizer.cpp:691-719; NO_SPEED_LIMIT == 0.0 (nav2_costmap_2d/costmap_filters/filter_values.hpp)
+  if (speed_limit == 0.0) {
+    h->c_vx_max = h->base_vx_max; h->c_vx_min = h->base_vx_min; h->c_vy = h->base_vy; h->c_wz = h->base_wz;
+  } else {
+    const double ratio = percentage ? speed_limit / 100.0 : speed_limit / h->base_vx_max;
+    h->c_vx_max = h->base_vx_max * ratio;
+    h->c_vx_min = h->base_vx_min * ratio;
+    h->c_vy = h->base_vy * ratio;
+    h->c_wz = h->base_wz * ratio;
+  }
+  return MPPI_OK;
+}
+
+int mppi_upload_costmap(
+  MppiHandle * h, uint32_t robot, const uint8_t * cells, uint32_t size_x, uint32_t size_y,
+  double resolution, double origin_x, double origin_y)
+{
+  if (!h || !cells || robot >= static_cast<uint32_t>(h->R) || size_x == 0 || size_y == 0 || !(resolution > 0.0)) {
+    if (h) {h->error = "bad costmap arguments";}
+    return MPPI_ERR_INVALID_ARGUMENT;
+  }
+  const uint32_t pitch = (size_x + 15u) & ~15u;
+  const size_t need = static_cast<size_t>(pitch) * size_y;
+  if (need > h->map_stride) {
+    // (re)allocate the per-robot slabs; previously uploaded maps are re-sent from their host copies
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->side));
+    if (h->d_map) {cudaFree(h->d_map); h->d_map = nullptr;}
+    if (h->h_map_stage) {cudaFreeHost(h->h_map_stage); h->h_map_stage = nullptr;}
+    h->map_stride = need;
+    CU_CHECK(h, cudaMalloc(&h->d_map, h->map_stride * h->R));
+    CU_CHECK(h, cudaMemset(h->d_map, 0, h->map_stride * h->R));
+    h->map_stage_bytes = static_cast<size_t>(size_x) * size_y;
+    CU_CHECK(h, cudaMallocHost(&h->h_map_stage, h->map_stage_bytes * h->R));
+    for (int r = 0; r < h->R; ++r) {
+      HostRobot & o = h->robots[r];
+      if (o.map_valid && static_cast<uint32_t>(r) != robot) {
+        CU_CHECK(h, cudaMemcpy2D(
+            h->d_map + h->map_stride * r, o.pitch, o.map_host.data(), o.size_x, o.size_x, o.size_y,
+            cudaMemcpyHostToDevice));
+      }
+    }
+  }
+  const size_t tight = static_cast<size_t>(size_x) * size_y;
+  if (tight > h->map_stage_bytes) {
+    CU_CHECK(h, cudaStreamSynchronize(h->side));
+    if (h->h_map_stage) {cudaFreeHost(h->h_map_stage); h->h_map_stage = nullptr;}
+    h->map_stage_bytes = tight;
+    CU_CHECK(h, cudaMallocHost(&h->h_map_stage, h->map_stage_bytes * h->R));
+  }
+  HostRobot & rb = h->robots[robot];
+  // the previous async copy out of this staging slab must have drained before it is overwritten
+  CU_CHECK(h, cudaStreamSynchronize(h->side));
+  uint8_t * stage = h->h_map_stage + h->map_stage_bytes * robot;
+  std::memcpy(stage, cells, tight);
+  rb.map_host.assign(cells, cells + tight);
+  rb.size_x = size_x; rb.size_y = size_y; rb.pitch = pitch;
+  rb.resolution = resolution; rb.origin_x = origin_x; rb.origin_y = origin_y;
+  rb.map_valid = true;
+  // pinned -> device on the side stream, tight rows -> 16-byte-pitched rows
+  CU_CHECK(h, cudaMemcpy2DAsync(
+      h->d_map + h->map_stride * robot, pitch, stage, size_x, size_x, size_y, cudaMemcpyHostToDevice, h->side));
+  CU_CHECK(h, cudaEventRecord(h->map_event, h->side));
+  h->map_event_pending = true;
+  return MPPI_OK;
+}
+
+int mppi_set_noise(
+  MppiHandle * h, uint32_t robot, const float * noises_vx, const float * noises_vy, const float * noises_wz)
+{
+  if (!h || robot >= static_cast<uint32_t>(h->R) || !noises_vx || !noises_wz) {return MPPI_ERR_INVALID_ARGUMENT;}
+  const size_t slab = static_cast<size_t>(h->B) * h->T;
+  CU_CHECK(h, cudaMemcpyAsync(h->d_noise[0] + robot * slab, noises_vx, slab * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (noises_vy) {
+    CU_CHECK(h, cudaMemcpyAsync(h->d_noise[1] + robot * slab, noises_vy, slab * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    CU_CHECK(h, cudaMemsetAsync(h->d_noise[1] + robot * slab, 0, slab * sizeof(float), h->stream));
+  }
+  CU_CHECK(h, cudaMemcpyAsync(h->d_noise[2] + robot * slab, noises_wz, slab * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  h->robots[robot].noise_injected = true;
+  return MPPI_OK;
+}
+
+int mppi_generate_noise(MppiHandle * h, uint32_t robot)
+{
+  if (!h || robot >= static_cast<uint32_t>(h->R)) {return MPPI_ERR_INVALID_ARGUMENT;}
+  int rc = generate_noise(h, static_cast<int>(robot));
+  if (rc != MPPI_OK) {return rc;}
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  return MPPI_OK;
+}
+
+int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
+{
+  if (!h || !in || !out) {return MPPI_ERR_INVALID_ARGUMENT;}
+  if (h->cfg.shard_world != 1) {
+    h->error = "mppi_optimize on a sharded handle: use the mppi_shard_* phases";
+    return MPPI_ERR_UNSUPPORTED;
+  }
+  int max_n = 1;
+  for (int r = 0; r < h->R; ++r) {max_n = std::max<int>(max_n, in[r].n_path);}
+  int rc = ensure_cycle_block(h, max_n);
+  if (rc != MPPI_OK) {return rc;}
+  if (h->cfg.regenerate_noises) {
+    // noise thread analogue (noise_generator.cpp:98-106): fresh noise for this cycle
+    for (int r = 0; r < h->R; ++r) {
+      if (!h->robots[r].noise_injected) {
+        rc = generate_noise(h, r);
+        if (rc != MPPI_OK) {return rc;}
+      }
+    }
+  }
+  for (int r = 0; r < h->R; ++r) {
+    out[r].retries = 0;
+    out[r].status = MPPI_OK;
+    rc = prepare_robot(h, r, in[r], -1, false);
+    if (rc != MPPI_OK) {return rc;}
+  }
+  const LaunchPlan plan = make_plan(h);
+  bool first = true;
+  while (true) {
+    rc = upload_cycle_block(h, h->stream);
+    if (rc != MPPI_OK) {return rc;}
+    if (first) {
+      // pristine copies for mppi_enqueue_resident
+      CU_CHECK(h, cudaMemcpyAsync(h->d_cycle_saved, h->d_cycle_block, h->cycle_block_bytes, cudaMemcpyDeviceToDevice, h->stream));
+      CU_CHECK(h, cudaMemcpyAsync(h->d_u_saved, h->d_u, sizeof(float) * 3 * h->T * h->R, cudaMemcpyDeviceToDevice, h->stream));
+      CU_CHECK(h, cudaMemcpyAsync(h->d_hist_saved, h->d_hist, sizeof(float) * 12 * h->R, cudaMemcpyDeviceToDevice, h->stream));
+      CU_CHECK(h, cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, h->stream));
+      first = false;
+    }
+    if (h->cfg.visualize) {
+      CU_CHECK(h, cudaMemsetAsync(h->d_collisions, 0, static_cast<size_t>(h->B) * h->R, h->stream));
+      if (h->d_critic_costs) {
+        CU_CHECK(h, cudaMemsetAsync(h->d_critic_costs, 0, sizeof(float) * h->cfg.n_critics * h->B * h->R, h->stream));
+      }
+    }
+    rc = wait_map(h, h->stream);
+    if (rc != MPPI_OK) {return rc;}
+    rc = enqueue_iterations(h, h->stream, plan);
+    if (rc != MPPI_OK) {return rc;}
+    CU_CHECK(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_stride * h->R, cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    bool any_retry = false;
+    for (int r = 0; r < h->R; ++r) {
+      if (!h->hcyc(r)->run) {continue;}  // finished in an earlier attempt
+      bool retry = false;
+      rc = finish_attempt(h, r, out[r], retry);
+      if (rc != MPPI_OK) {return rc;}
+      any_retry = any_retry || retry;
+    }
+    if (!any_retry) {break;}
+  }
+  h->have_cycle = true;
+  return MPPI_OK;
+}
+
+int mppi_score_tensors(
+  MppiHandle * h, uint32_t robot, const MppiCycleIn * in,
+  const float * vx, const float * vy, const float * wz,
+  const float * x, const float * y, const float * yaw,
+  int32_t furthest_reached_path_point,
+  float * costs, uint8_t * collisions, int32_t * fail_flag, int32_t * furthest_out)
+{
+  if (!h || !in || !vx || !wz || !x || !y || !yaw || !costs || robot >= static_cast<uint32_t>(h->R)) {
+    return MPPI_ERR_INVALID_ARGUMENT;
+  }
+  int rc = ensure_cycle_block(h, std::max<int>(1, in->n_path));
+  if (rc != MPPI_OK) {return rc;}
+  const size_t bt_all = static_cast<size_t>(h->R) * h->B * h->T;
+  for (int i = 0; i < 6; ++i) {
+    if (!h->d_state[i]) {
+      CU_CHECK(h, cudaMalloc(&h->d_state[i], bt_all * sizeof(float)));
+      CU_CHECK(h, cudaMemset(h->d_state[i], 0, bt_all * sizeof(float)));
+    }
+  }
+  const size_t slab = static_cast<size_t>(h->B) * h->T;
+  const float * src[6] = {vx, vy, wz, x, y, yaw};
+  for (int i = 0; i < 6; ++i) {
+    float * dst = h->d_state[i] + slab * robot;
+    if (src[i]) {
+      CU_CHECK(h, cudaMemcpyAsync(dst, src[i], slab * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    } else {
+      CU_CHECK(h, cudaMemsetAsync(dst, 0, slab * sizeof(float), h->stream));
+    }
+  }
+  // only `robot` runs: every other robot's cycle gets run = 0
+  for (int r = 0; r < h->R; ++r) {
+    if (static_cast<uint32_t>(r) == robot) {
+      rc = prepare_robot(h, r, *in, furthest_reached_path_point, true);
+      if (rc != MPPI_OK) {return rc;}
+    } else {
+      h->hcyc(r)->run = 0;
+    }
+  }
+  const LaunchPlan plan = make_plan(h);
+  rc = upload_cycle_block(h, h->stream);
+  if (rc != MPPI_OK) {return rc;}
+  CU_CHECK(h, cudaMemcpyAsync(h->d_costs + static_cast<size_t>(robot) * h->B, costs, sizeof(float) * h->B, cudaMemcpyHostToDevice, h->stream));
+  CU_CHECK(h, cudaMemsetAsync(h->d_collisions + static_cast<size_t>(robot) * h->B, 0, h->B, h->stream));
+  rc = wait_map(h, h->stream);
+  if (rc != MPPI_OK) {return rc;}
+  KArgs a = make_args(h);
+  CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, h->holo, true, plan.block_a, h->stream));
+  CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, true, plan.block_a, h->stream));
+  h->launches += 2;
+  CU_CHECK(h, cudaMemcpyAsync(costs, h->d_costs + static_cast<size_t>(robot) * h->B, sizeof(float) * h->B, cudaMemcpyDeviceToHost, h->stream));
+  if (collisions) {
+    CU_CHECK(h, cudaMemcpyAsync(collisions, h->d_collisions + static_cast<size_t>(robot) * h->B, h->B, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU_CHECK(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_stride * h->R, cudaMemcpyDeviceToHost, h->stream));
+  // reset the reduction words this call dirtied (the finalize kernel does it on the normal path)
+  {
+    int32_t init[RED_WORDS] = {0, INT32_MIN, 0, 0, INT32_MIN, 0, 0, 0};
+    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    CU_CHECK(h, cudaMemcpy(h->d_red + robot * RED_WORDS, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
+  const DevOutHeader * hdr = reinterpret_cast<const DevOutHeader *>(h->h_out + h->out_stride * robot);
+  if (fail_flag) {*fail_flag = hdr->fail_flag;}
+  if (furthest_out) {*furthest_out = hdr->furthest;}
+  h->have_cycle = false;
+  return MPPI_OK;
+}
+
+int mppi_get_tensor(MppiHandle * h, uint32_t robot, int32_t which, void * dst, size_t dst_bytes)
+{
+  if (!h || !dst || robot >= static_cast<uint32_t>(h->R)) {return MPPI_ERR_INVALID_ARGUMENT;}
+  const size_t B = h->B, T = h->T, slab = B * T;
+  const void * src = nullptr;
+  size_t bytes = 0;
+  auto need = [&](const void * p, const char * what) -> int {
+      if (!p) {h->error = std::string(what) + " is not kept (enable materialize_tensors / visualize / debug_cells)"; return MPPI_ERR_UNSUPPORTED;}
+      return MPPI_OK;
+    };
+  int rc = MPPI_OK;
+  switch (which) {
+    case MPPI_TENSOR_VX: rc = need(h->d_state[0], "state.vx"); src = h->d_state[0] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_VY: rc = need(h->d_state[1], "state.vy"); src = h->d_state[1] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_WZ: rc = need(h->d_state[2], "state.wz"); src = h->d_state[2] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_X: rc = need(h->d_state[3], "trajectories.x"); src = h->d_state[3] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_Y: rc = need(h->d_state[4], "trajectories.y"); src = h->d_state[4] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_YAW: rc = need(h->d_state[5], "trajectories.yaws"); src = h->d_state[5] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_CVX: rc = need(h->d_cv[0], "state.cvx"); src = h->d_cv[0] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_CVY: rc = need(h->d_cv[1], "state.cvy"); src = h->d_cv[1] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_CWZ: rc = need(h->d_cv[2], "state.cwz"); src = h->d_cv[2] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_NOISE_VX: src = h->d_noise[0] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_NOISE_VY: src = h->d_noise[1] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_NOISE_WZ: src = h->d_noise[2] + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_COSTS: src = h->d_costs + B * robot; bytes = B * 4; break;
+    case MPPI_TENSOR_SOFTMAX: src = h->d_softmax + B * robot; bytes = B * 4; break;
+    case MPPI_TENSOR_CRITIC_COSTS:
+      rc = need(h->d_critic_costs, "critic costs");
+      src = h->d_critic_costs + static_cast<size_t>(h->cfg.n_critics) * B * robot; bytes = h->cfg.n_critics * B * 4; break;
+    case MPPI_TENSOR_COLLISIONS: src = h->d_collisions + B * robot; bytes = B; break;
+    case MPPI_TENSOR_COST_CELLS:
+      rc = need(h->d_dbg_cost, "cost cells");
+      src = h->d_dbg_cost + static_cast<size_t>(h->cc_ns) * B * robot; bytes = static_cast<size_t>(h->cc_ns) * B * 4; break;
+    case MPPI_TENSOR_OBSTACLE_CELLS:
+      rc = need(h->d_dbg_obs, "obstacle cells"); src = h->d_dbg_obs + slab * robot; bytes = slab * 4; break;
+    default: h->error = "unknown tensor"; return MPPI_ERR_INVALID_ARGUMENT;
+  }
+  if (rc != MPPI_OK) {return rc;}
+  if (bytes != dst_bytes) {h->error = "dst_bytes does not match the tensor size"; return MPPI_ERR_INVALID_ARGUMENT;}
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  CU_CHECK(h, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return MPPI_OK;
+}
+
+int mppi_get_control_sequence(MppiHandle * h, uint32_t robot, float * vx, float * vy, float * wz)
+{
+  if (!h || robot >= static_cast<uint32_t>(h->R)) {return MPPI_ERR_INVALID_ARGUMENT;}
+  const size_t T = h->T;
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  const float * u = h->d_u + robot * 3 * T;
+  if (vx) {CU_CHECK(h, cudaMemcpy(vx, u, T * 4, cudaMemcpyDeviceToHost));}
+  if (vy) {CU_CHECK(h, cudaMemcpy(vy, u + T, T * 4, cudaMemcpyDeviceToHost));}
+  if (wz) {CU_CHECK(h, cudaMemcpy(wz, u + 2 * T, T * 4, cudaMemcpyDeviceToHost));}
+  return MPPI_OK;
+}
+
+int mppi_set_control_sequence(MppiHandle * h, uint32_t robot, const float * vx, const float * vy, const float * wz)
+{
+  if (!h || robot >= static_cast<uint32_t>(h->R)) {return MPPI_ERR_INVALID_ARGUMENT;}
+  const size_t T = h->T;
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  float * u = h->d_u + robot * 3 * T;
+  if (vx) {CU_CHECK(h, cudaMemcpy(u, vx, T * 4, cudaMemcpyHostToDevice));}
+  if (vy) {CU_CHECK(h, cudaMemcpy(u + T, vy, T * 4, cudaMemcpyHostToDevice));}
+  if (wz) {CU_CHECK(h, cudaMemcpy(u + 2 * T, wz, T * 4, cudaMemcpyHostToDevice));}
+  return MPPI_OK;
+}
+
+int mppi_enqueue_resident(MppiHandle * h, void * cuda_stream)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  if (!h->have_cycle) {h->error = "mppi_enqueue_resident needs a preceding mppi_optimize"; return MPPI_ERR_NOT_READY;}
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  // restore the state the cycle started from, so every replay does identical work
+  CU_CHECK(h, cudaMemcpyAsync(h->d_cycle_block, h->d_cycle_saved, h->cycle_block_bytes, cudaMemcpyDeviceToDevice, s));
+  CU_CHECK(h, cudaMemcpyAsync(h->d_u, h->d_u_saved, sizeof(float) * 3 * h->T * h->R, cudaMemcpyDeviceToDevice, s));
+  CU_CHECK(h, cudaMemcpyAsync(h->d_hist, h->d_hist_saved, sizeof(float) * 12 * h->R, cudaMemcpyDeviceToDevice, s));
+  CU_CHECK(h, cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, s));
+  const LaunchPlan plan = make_plan(h);
+  return enqueue_iterations(h, s, plan);
+}
+
+uint64_t mppi_launch_count(const MppiHandle * h) {return h ? h->launches : 0;}
+
+int mppi_set_kernel_timing(MppiHandle * h, int enabled)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  h->timing = enabled != 0;
+  h->timing_used = 0;
+  return MPPI_OK;
+}
+
+int mppi_kernel_time_ms(MppiHandle * h, int reset, double * ms_per_launch, uint64_t * launches)
+{
+  if (!h || !ms_per_launch) {return MPPI_ERR_INVALID_ARGUMENT;}
+  CU_CHECK(h, cudaDeviceSynchronize());
+  double total = 0.0;
+  for (size_t i = 0; i < h->timing_used; ++i) {
+    float ms = 0.0f;
+    CU_CHECK(h, cudaEventElapsedTime(&ms, h->timing_events[i].first, h->timing_events[i].second));
+    total += ms;
+  }
+  *ms_per_launch = h->timing_used ? total / static_cast<double>(h->timing_used) : 0.0;
+  if (launches) {*launches = h->timing_used;}
+  if (reset) {h->timing_used = 0;}
+  return MPPI_OK;
+}
+
+void * mppi_stream(MppiHandle * h) {return h ? static_cast<void *>(h->stream) : nullptr;}
+
+int mppi_device_synchronize(MppiHandle * h)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  CU_CHECK(h, cudaStreamSynchronize(h->side));
+  return MPPI_OK;
+}
+
+// ---------------------------------------------------------------- batch sharding phases
+
+int mppi_shard_buffers(
+  MppiHandle * h, void ** ar1, size_t * ar1_words, void ** ar2_slot, size_t * ar2_words, void ** ar2_all)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  if (ar1) {*ar1 = h->d_red;}
+  if (ar1_words) {*ar1_words = static_cast<size_t>(RED_WORDS) * h->R;}
+  if (ar2_slot) {*ar2_slot = h->d_slot;}
+  if (ar2_words) {*ar2_words = static_cast<size_t>(2 + 3 * h->T) * h->R;}
+  if (ar2_all) {*ar2_all = h->d_slot_all;}
+  return MPPI_OK;
+}
+
+int mppi_shard_begin(MppiHandle * h, const MppiCycleIn * in)
+{
+  if (!h || !in) {return MPPI_ERR_INVALID_ARGUMENT;}
+  int max_n = 1;
+  for (int r = 0; r < h->R; ++r) {max_n = std::max<int>(max_n, in[r].n_path);}
+  int rc = ensure_cycle_block(h, max_n);
+  if (rc != MPPI_OK) {return rc;}
+  for (int r = 0; r < h->R; ++r) {
+    rc = prepare_robot(h, r, in[r], -1, false);
+    if (rc != MPPI_OK) {return rc;}
+  }
+  rc = upload_cycle_block(h, h->stream);
+  if (rc != MPPI_OK) {return rc;}
+  CU_CHECK(h, cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, h->stream));
+  return wait_map(h, h->stream);
+}
+
+int mppi_shard_rollout(MppiHandle * h)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  const LaunchPlan plan = make_plan(h);
+  KArgs a = make_args(h);
+  CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, h->holo, false, plan.block_a, h->stream));
+  h->launches += 1;
+  return MPPI_OK;
+}
+
+int mppi_shard_score(MppiHandle * h)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  const LaunchPlan plan = make_plan(h);
+  KArgs a = make_args(h);
+  CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, false, plan.block_a, h->stream));
+  CU_CHECK(h, mppi_launch_softmax_partial(a, h->holo, h->stream));
+  CU_CHECK(h, mppi_launch_finalize(a, h->holo, 1, h->stream));
+  h->launches += 3;
+  return MPPI_OK;
+}
+
+int mppi_shard_update(MppiHandle * h, int last_iteration)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  KArgs a = make_args(h);
+  a.last_iteration = last_iteration ? 1 : 0;
+  CU_CHECK(h, mppi_launch_finalize(a, h->holo, 2, h->stream));
+  h->launches += 1;
+  return MPPI_OK;
+}
+
+int mppi_shard_end(MppiHandle * h, MppiCycleOut * out)
+{
+  if (!h || !out) {return MPPI_ERR_INVALID_ARGUMENT;}
+  CU_CHECK(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_stride * h->R, cudaMemcpyDeviceToHost, h->stream));
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  int result = MPPI_OK;
+  for (int r = 0; r < h->R; ++r) {
+    bool retry = false;
+    out[r].status = MPPI_OK;
+    int rc = finish_attempt(h, r, out[r], retry);
+    if (rc != MPPI_OK) {return rc;}
+    if (retry) {result = 1;}  // caller re-uploads (mppi_shard_retry) and repeats the phases
+  }
+  if (result == 1) {
+    int rc = upload_cycle_block(h, h->stream);
+    if (rc != MPPI_OK) {return rc;}
+  }
+  return result;
+}
+
+}  // extern "C"

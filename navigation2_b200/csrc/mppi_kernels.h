@@ -1,0 +1,42 @@
+// mppi_kernels.h — launch interface between the host runtime (mppi_capi.cu) and mppi_kernels.cu.
+#ifndef NAVIGATION2_B200_CSRC_MPPI_KERNELS_H_
+#define NAVIGATION2_B200_CSRC_MPPI_KERNELS_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mppi_device.h"
+
+// dynamic shared-memory layout of the rollout+score kernel (byte offsets)
+struct KSmemA
+{
+  uint32_t off_u;      // float u[3][T]
+  uint32_t off_path;   // float path x / y / integrated distance, path_cap each
+  uint32_t off_lut;    // float obstacle distance LUT [2][256]
+  uint32_t off_ring;   // float delay ring [3][ring_depth][block]
+  uint32_t off_win;    // uint8 costmap window
+  int32_t path_cap;
+  int32_t ring_depth;
+  uint32_t total;
+};
+
+struct KSmemB
+{
+  int32_t path_cap;
+  uint32_t total;
+};
+
+KSmemA mppi_smem_layout_a(int T, int path_cap, bool obstacles, int ring_depth, int block, int win_bytes);
+
+cudaError_t mppi_launch_rollout_score(
+  const KArgs & a, const KSmemA & sm, bool holo, bool from_tensors, int block, cudaStream_t stream);
+cudaError_t mppi_launch_path_score(
+  const KArgs & a, int path_cap, bool holo, bool from_tensors, int block, cudaStream_t stream);
+cudaError_t mppi_launch_softmax_partial(const KArgs & a, bool holo, cudaStream_t stream);
+// shard_stage: 0 single GPU, 1 reduce partials into this rank's slot, 2 combine slots + finalize
+cudaError_t mppi_launch_finalize(const KArgs & a, bool holo, int shard_stage, cudaStream_t stream);
+cudaError_t mppi_launch_philox(
+  float * nvx, float * nvy, float * nwz, int B, int T, int R, int b_offset, uint64_t seed,
+  uint32_t epoch, float std_vx, float std_vy, float std_wz, bool holo, cudaStream_t stream);
+
+#endif  // NAVIGATION2_B200_CSRC_MPPI_KERNELS_H_
