@@ -1,0 +1,501 @@
+#!/usr/bin/env python
+"""bench.py — MPPI trajectory-steps scored per second (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c3|c4|c5]
+
+A *step* is one Optimizer::optimize() (iteration_count iterations of rollout -> score -> update)
+over one batch of synthetic input.  Default workload (N=1): BASELINE.json configs[1], DiffDrive
+2000 x 56, model_dt 0.05, default critics with the bring-up yaml weights, 400x400 costmap @0.05 m,
+seeded injected noise.  N>1 (torchrun, one rank per GPU): every rank drives its own independent
+controller on the same workload — "fleets of independent controllers are partitioned one robot-set
+per GPU", no data-path collective, weak scaling.  `--workload c4` is the 1M x 56 batch sharded over
+the ranks with the NCCL exchanges of SURVEY.md §8e (strong scaling); `--workload c5` is the fleet.
+
+Printed JSON (one line, rank 0):
+  value      trajectory-steps/s, inputs resident in HBM, CUDA-event timed, L2 flushed between steps
+  e2e        the same metric through the public API (Optimizer.evalControl) with HOST buffers:
+             costmap + cycle inputs H2D from pinned memory and the command/control sequence D2H
+             inside the timed region
+  roofline   dominant kernel (rollout+score) against the measured HBM peak
+  cpu_baseline  the CPU oracle (a restatement, `kind: port`) on this box's host cores, 1 thread
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "MPPI trajectory-steps scored/sec at batch 2000x56; p50 optimize() latency"
+UNIT = "trajectory-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c1", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--robots", type=int, default=512, help="robots per GPU for --workload c5")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large-batch", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- workloads
+
+def workload_c1():
+    """BASELINE.json configs[0]/[1]."""
+    from navigation2_b200 import params as P, scenarios as S
+    import navigation2_b200 as nb
+    cfg = P.nav2_bringup_config()
+    cells = S.block_costmap(400, 400, 0.05, seed=1, keep_clear=(10.0, 10.0))
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    inp = nb.CycleInput(pose=(10.0, 10.0, 0.0), speed=(0.2, 0.0, 0.0), path=path, goal=tuple(path[-1]),
+                        goal_checker_xy_tolerance=0.25)
+    return dict(name="C1 DiffDrive 2000x56, default critics (yaml weights), 400x400 costmap @0.05 m, injected seeded noise",
+                cfg=cfg, cells=cells, resolution=0.05, origin=(0.0, 0.0), inp=inp, holo=False)
+
+
+def workload_c3(model="omni"):
+    """BASELINE.json configs[2]: Omni (or Ackermann) 16384 x 100, full critic set incl. Obstacles + inflation."""
+    from navigation2_b200 import params as P, scenarios as S
+    import navigation2_b200 as nb
+    critics = ["ConstraintCritic", "CostCritic", "GoalCritic", "GoalAngleCritic", "ObstaclesCritic", "PathAlignCritic",
+               "PathFollowCritic", "PathAngleCritic", "PreferForwardCritic", "TwirlingCritic", "VelocityDeadbandCritic"]
+    cfg = P.make_config({"batch_size": 16384, "time_steps": 100, "motion_model": model, "controller_frequency": 20.0},
+                        critics, P.NAV2_BRINGUP_CRITIC_PARAMS, robot_radius=0.22,
+                        inflation={"cost_scaling_factor": 3.0, "inflation_radius": 0.70})
+    cells = S.block_costmap(400, 400, 0.05, seed=1, keep_clear=(10.0, 10.0))
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=140)
+    inp = nb.CycleInput(pose=(10.0, 10.0, 0.0), speed=(0.2, 0.0, 0.0), path=path, goal=tuple(path[-1]),
+                        goal_checker_xy_tolerance=0.25)
+    return dict(name=f"C3 {model} 16384x100, full critic set incl. Obstacles+inflation, 400x400 costmap",
+                cfg=cfg, cells=cells, resolution=0.05, origin=(0.0, 0.0), inp=inp, holo=model == "omni")
+
+
+def large_batch_config(batch, world=1, rank=0):
+    from navigation2_b200 import params as P
+    return P.nav2_bringup_config(batch_size=batch, shard_world=world, shard_rank=rank)
+
+
+# ----------------------------------------------------------------------------- helpers
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks and throttle reasons DURING the timed region."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def setup_engine(wl, cfg=None, seed=42):
+    import navigation2_b200 as nb
+    from navigation2_b200 import scenarios as S
+    cfg = cfg or wl["cfg"]
+    opt = nb.Optimizer(cfg)  # raises if the CUDA library / device is missing: no fallback
+    R = int(cfg.n_robots)
+    B = int(cfg.batch_size) // int(cfg.shard_world)
+    for r in range(R):
+        opt.setCostmap(wl["cells"], wl["resolution"], wl["origin"][0], wl["origin"][1], robot=r)
+    if B * int(cfg.time_steps) * R <= (1 << 24):
+        for r in range(R):
+            nvx, nvy, nwz = S.seeded_noise(B, int(cfg.time_steps), (cfg.vx_std, cfg.vy_std, cfg.wz_std),
+                                           seed=seed + r, holonomic=wl["holo"])
+            opt.setNoise(nvx, nvy, nwz, robot=r)
+    # else: keep the Philox noise the library drew at reset (seed + global trajectory index)
+    return opt
+
+
+def algorithmic_bytes_kernel_a(cfg, win_bytes):
+    """noise columns read once (4 B x axes per trajectory-step) + 5 B per trajectory
+    (cost + collision flag) + the staged costmap window once."""
+    from navigation2_b200 import capi
+    axes = 3 if cfg.motion_model == capi.MPPI_MODEL_OMNI else 2
+    B = int(cfg.batch_size) // int(cfg.shard_world)
+    R = int(cfg.n_robots)
+    return R * (B * int(cfg.time_steps) * 4 * axes + 5 * B + win_bytes)
+
+
+def time_resident(opt, steps, warmup, flush, stream):
+    """K resident steps, each bracketed by CUDA events on the launching stream, L2 flushed between."""
+    import torch
+    for _ in range(warmup):
+        if flush is not None:
+            flush.zero_()
+        opt.enqueueResident(stream.cuda_stream)
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for i in range(steps):
+        if flush is not None:
+            flush.zero_()  # > L2 (126 MB): the next step starts cold
+        starts[i].record(stream)
+        opt.enqueueResident(stream.cuda_stream)
+        stops[i].record(stream)
+    torch.cuda.synchronize()
+    return np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])  # ms
+
+
+# ----------------------------------------------------------------------------- reference arm
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path cannot be built here (no ROS 2 / Eigen);
+    this arm times the oracle port (oracle/, -O3 -mavx2 -mfma, the reference's flags) on the host
+    cores.  The reference control path is single-threaded, so is this."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.binding import OracleOptimizer
+    from navigation2_b200 import scenarios as S
+    wl = workload_c1() if args.workload in ("c1", "c4", "c5") else workload_c3()
+    cfg = wl["cfg"]
+    o = OracleOptimizer(cfg, fast=True)
+    o.setCostmap(wl["cells"], wl["resolution"], *wl["origin"])
+    nvx, nvy, nwz = S.seeded_noise(int(cfg.batch_size), int(cfg.time_steps), (cfg.vx_std, cfg.vy_std, cfg.wz_std),
+                                   holonomic=wl["holo"])
+    o.setNoise(nvx, nvy, nwz)
+    units = int(cfg.batch_size) * int(cfg.time_steps) * int(cfg.iteration_count)
+    for _ in range(args.warmup):
+        o.evalControl(wl["inp"])
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        o.evalControl(wl["inp"])
+        times.append(time.perf_counter() - t0)
+    times = np.array(times)
+    total = float(times.sum())
+    value = units * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "p50_ms": float(np.median(times) * 1e3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "batch_size": int(cfg.batch_size), "time_steps": int(cfg.time_steps),
+                   "iteration_count": int(cfg.iteration_count)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{args.steps} full evalControl cycles of the workload (oracle port, g++ -O3 -mavx2 -mfma, 1 thread; "
+                                   "the reference's Eigen build needs ROS 2 and cannot be compiled here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cpu": cpu_model(), "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ----------------------------------------------------------------------------- our arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from navigation2_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the optimiser has no CPU path to measure")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.workload == "c4":
+        return run_c4(args, world, rank, local_rank)
+
+    wl = workload_c1() if args.workload in ("c1", "c5") else workload_c3()
+    cfg = wl["cfg"]
+    if args.workload == "c5":
+        from navigation2_b200 import params as P, scenarios as S
+        cfg = P.nav2_bringup_config(n_robots=args.robots)
+        wl = dict(wl)
+        wl["cfg"] = cfg
+        wl["cells"] = S.block_costmap(200, 200, 0.05, seed=1 + rank, keep_clear=(5.0, 5.0))
+        import navigation2_b200 as nb
+        path = S.arc_path((5.0, 5.0, 0.0), n_points=100)
+        wl["inp"] = nb.CycleInput(pose=(5.0, 5.0, 0.0), speed=(0.2, 0.0, 0.0), path=path, goal=tuple(path[-1]),
+                                  goal_checker_xy_tolerance=0.25)
+        wl["name"] = f"C5 fleet: {args.robots} independent robots per GPU, own 200x200 costmap + path each, batch 2000x56"
+    R = int(cfg.n_robots)
+    B, T, iters = int(cfg.batch_size), int(cfg.time_steps), int(cfg.iteration_count)
+    units_per_step = R * B * T * iters
+
+    opt = setup_engine(wl, seed=42 + 1000 * rank)
+    inputs = wl["inp"] if R == 1 else [wl["inp"]] * R
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # 256 MiB > 126 MB L2
+
+    # first call through the public API: uploads the cycle inputs that the resident path replays
+    opt.evalControl(inputs)
+    opt.reset()
+    opt.evalControl(inputs)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- value: resident inputs, CUDA events on the launching stream, L2 flushed between steps ----
+    launches0 = opt.launchCount()
+    opt.setKernelTiming(False)
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    step_ms = time_resident(opt, args.steps, args.warmup, flush, stream)
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = opt.launchCount() - launches0
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    total_ms = float(step_ms.sum())
+    if distributed:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * units_per_step * args.steps / (total_ms * 1e-3)
+
+    # hot-L2 variant (no flush) for context: what a 20 Hz controller loop actually sees
+    hot_ms = time_resident(opt, args.steps, 3, None, stream)
+
+    # ---- dominant kernel (rollout+score) timed alone with CUDA events inside the library ----
+    opt.setKernelTiming(True)
+    time_resident(opt, min(args.steps, 50), 3, flush, stream)
+    ka_ms, ka_n = opt.kernelTimeMs(reset=True)
+    opt.setKernelTiming(False)
+
+    # ---- e2e: public API, host buffers, H2D costmap + inputs and D2H result inside the timed region ----
+    opt.reset()
+    for _ in range(args.warmup):
+        for r in range(R):
+            opt.setCostmap(wl["cells"], wl["resolution"], *wl["origin"], robot=r)
+        opt.evalControl(inputs)
+    e2e_times = []
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        for r in range(R):
+            opt.setCostmap(wl["cells"], wl["resolution"], *wl["origin"], robot=r)  # pinned staging -> cudaMemcpy2DAsync, side stream
+        opt.evalControl(inputs)                                                    # H2D cycle block, kernels, D2H command + sequence
+        e2e_times.append(time.perf_counter() - t0)
+    torch.cuda.synchronize()
+    e2e_times = np.array(e2e_times)
+    e2e_total = float(e2e_times.sum())
+    if distributed:
+        t = torch.tensor([e2e_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_value = world * units_per_step * args.steps / e2e_total
+    n_path = np.asarray(wl["inp"].path).reshape(-1, 3).shape[0]
+    max_path = 256
+    while max_path < n_path:
+        max_path *= 2
+    h2d = R * (wl["cells"].size + 512 + 17 * max_path)       # costmap + DevCycle + path arrays/validity
+    d2h = R * (32 + 6 * T * 4)                               # header + control sequence + optimal trajectory
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_peak_gbs()
+    win = 0
+    try:
+        half = min(max(int(np.ceil((0.5 * T * cfg.model_dt * 1.25 + cfg.circumscribed_radius + 4 * wl["resolution"]) / wl["resolution"])), 8), 96)
+        win = ((2 * half + 1 + 15) // 16 * 16) * (2 * half + 1)
+    except Exception:
+        pass
+    alg_bytes = algorithmic_bytes_kernel_a(cfg, win)
+    achieved = alg_bytes / (ka_ms * 1e-3) / 1e9 if ka_ms > 0 else 0.0
+    roofline = {"kernel": "k_rollout_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": ka_ms, "launches_timed": ka_n, "peak_source": peak_src,
+                "note": "C1 moves <1 MB per launch and is launch/latency-bound (SURVEY.md §8d); see roofline_large_batch "
+                        "for the same kernel on a batch larger than L2"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "batch_size": B, "time_steps": T, "iteration_count": iters, "n_robots_per_gpu": R,
+                   "parallelism": "independent controller per GPU, no collective" if world > 1 else "single GPU",
+                   "l2": "256 MiB buffer written between timed steps (L2 flushed)"},
+        "p50_optimize_us": float(np.median(step_ms) * 1e3),
+        "p50_optimize_us_hot_l2": float(np.median(hot_ms) * 1e3),
+        "value_hot_l2": world * units_per_step / (float(np.mean(hot_ms)) * 1e-3),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "p50_latency_us": float(np.median(e2e_times) * 1e6), "mean_latency_us": float(np.mean(e2e_times) * 1e6)},
+        "gpu_launches": int(launches_timed),
+        "roofline": roofline,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and not args.no_large_batch and args.workload == "c1":
+        line["roofline_large_batch"] = large_batch_roofline(peak, peak_src, stream, flush)
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(wl)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    opt.shutdown()
+    if distributed:
+        dist.destroy_process_group()
+
+
+def large_batch_roofline(peak, peak_src, stream, flush):
+    """The same rollout+score kernel on one GPU's worth of BASELINE.json configs[3] (2^20 x 56, Philox
+    noise): working set (2 x 235 MB of noise) >> L2, so this is the HBM-bound regime."""
+    import torch
+    import navigation2_b200 as nb
+    wl = workload_c1()
+    cfg = large_batch_config(1 << 20)
+    opt = setup_engine(wl, cfg=cfg)
+    opt.evalControl(wl["inp"])
+    opt.setKernelTiming(True)
+    step_ms = time_resident(opt, 10, 3, flush, stream)
+    ka_ms, ka_n = opt.kernelTimeMs(reset=True)
+    win = 0
+    alg = algorithmic_bytes_kernel_a(cfg, win)
+    achieved = alg / (ka_ms * 1e-3) / 1e9
+    units = int(cfg.batch_size) * int(cfg.time_steps)
+    out = {"kernel": "k_rollout_score", "workload": "DiffDrive 1048576x56 (configs[3] on one GPU), default critics, Philox noise",
+           "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+           "algorithmic_bytes_per_launch": alg, "kernel_ms": ka_ms, "launches_timed": ka_n, "peak_source": peak_src,
+           "step_ms": float(np.mean(step_ms)), "value": units / (float(np.mean(step_ms)) * 1e-3), "unit_value": UNIT}
+    opt.shutdown()
+    return out
+
+
+def cpu_baseline(wl):
+    """The oracle port (kind "port": the reference's Eigen build needs ROS 2) on one host core,
+    ~10-20 s of the same workload."""
+    from oracle.binding import OracleOptimizer
+    from navigation2_b200 import scenarios as S
+    cfg = wl["cfg"]
+    B = int(cfg.batch_size)
+    if int(cfg.n_robots) != 1:
+        from navigation2_b200 import params as P
+        cfg = P.nav2_bringup_config()
+        B = int(cfg.batch_size)
+    o = OracleOptimizer(cfg, fast=True)
+    o.setCostmap(wl["cells"], wl["resolution"], *wl["origin"])
+    nvx, nvy, nwz = S.seeded_noise(B, int(cfg.time_steps), (cfg.vx_std, cfg.vy_std, cfg.wz_std), holonomic=wl["holo"])
+    o.setNoise(nvx, nvy, nwz)
+    sec = o.timeOptimize(wl["inp"], 20)
+    cycles = int(min(max(12.0 / max(sec, 1e-6), 20), 20000))
+    sec = o.timeOptimize(wl["inp"], cycles)
+    units = B * int(cfg.time_steps) * int(cfg.iteration_count)
+    o.shutdown()
+    return {"value": units / sec, "unit": UNIT, "cores": 1, "kind": "port", "ms_per_optimize": sec * 1e3,
+            "sample": f"{cycles} evalControl cycles of the same workload (~{cycles * sec:.0f} s), oracle/ C++ restatement, "
+                      "g++ -O3 -mavx2 -mfma, single thread like the reference's control path",
+            "host_cpu": cpu_model(), "host_cores": os.cpu_count()}
+
+
+def run_c4(args, world, rank, local_rank):
+    """BASELINE.json configs[3]: 2^20 x 56 sharded along the trajectory axis; per iteration one MAX
+    all-reduce of the reduction words and one all-gather of (min, sum, weighted control sums)."""
+    import torch
+    import torch.distributed as dist
+    from navigation2_b200.sharded import ShardedOptimizer
+    wl = workload_c1()
+    batch = 1 << 20
+    cfg = large_batch_config(batch, world=world, rank=rank)
+    opt = ShardedOptimizer(cfg)
+    opt.setCostmap(wl["cells"], wl["resolution"], *wl["origin"])
+    stream = torch.cuda.current_stream()
+    for _ in range(args.warmup):
+        opt.evalControl(wl["inp"])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        opt.evalControl(wl["inp"])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    units = batch * int(cfg.time_steps) * int(cfg.iteration_count)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": units * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4 DiffDrive 1048576x56 sharded along the trajectory axis, Philox noise keyed by global id",
+                       "parallelism": f"batch shard x{world}; per iteration 1 all-reduce (MAX, 8 words) + 1 all-gather (170 floats)",
+                       "l2": "inputs (470 MB of noise per GPU at N=1) larger than L2"},
+            "gpu_launches": int(opt.launchCount())}), flush=True)
+    opt.shutdown()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    from navigation2_b200 import build
+    build.build_all()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

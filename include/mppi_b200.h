@@ -235,6 +235,24 @@ typedef enum MppiTensor
   MPPI_TENSOR_SOFTMAX = 17          /* float[B]: unnormalised softmax weights exp(-(c - min)/temperature) */
 } MppiTensor;
 
+/*
+ * Everything mppi::Optimizer carries from one evalControl call to the next, besides the noise:
+ * control_sequence_, control_history_ (optimizer.hpp:309-310), last_command_vel_ (:331), the
+ * motion model's command-history ring buffers (motion_models.hpp:246-248) and fallback()'s retry
+ * counter (optimizer.cpp:283).  The reference has no checkpoint/resume; this is
+ * the hand-over used to migrate a robot between handles / GPUs and to start two implementations
+ * from bit-identical state in the parity tests.
+ */
+typedef struct MppiOptimizerState
+{
+  double last_command_vel[3];                    /* vx, vy, wz */
+  float control_history[12];                     /* 4 x (vx, vy, wz), oldest first */
+  float cmd_history_vx[MPPI_MAX_DELAY_STEPS];    /* newest last; only offsetSteps(delay) entries are used */
+  float cmd_history_vy[MPPI_MAX_DELAY_STEPS];
+  float cmd_history_wz[MPPI_MAX_DELAY_STEPS];
+  uint32_t fallback_counter;
+} MppiOptimizerState;
+
 typedef struct MppiHandle MppiHandle;
 
 /* ---- configuration helpers (no GPU needed) ---- */
@@ -252,6 +270,7 @@ size_t mppi_sizeof_config(void);
 size_t mppi_sizeof_critic_params(void);
 size_t mppi_sizeof_cycle_in(void);
 size_t mppi_sizeof_cycle_out(void);
+size_t mppi_sizeof_optimizer_state(void);
 /* InflationLayer::computeCost (nav2_costmap_2d/include/nav2_costmap_2d/inflation_layer.hpp:121-135) */
 uint8_t mppi_inflation_compute_cost(
   double distance_cells, double resolution, double inscribed_radius, double cost_scaling_factor);
@@ -320,6 +339,9 @@ int mppi_get_tensor(MppiHandle * h, uint32_t robot, int32_t which, void * dst, s
 int mppi_get_control_sequence(MppiHandle * h, uint32_t robot, float * vx, float * vy, float * wz);
 int mppi_set_control_sequence(
   MppiHandle * h, uint32_t robot, const float * vx, const float * vy, const float * wz);
+/* Save / restore the carried state (control sequence excluded: use the two calls above). */
+int mppi_get_state(MppiHandle * h, uint32_t robot, MppiOptimizerState * state);
+int mppi_set_state(MppiHandle * h, uint32_t robot, const MppiOptimizerState * state);
 
 /* ---- resident / measurement path (bench.py `value`, ncu) ---- */
 
@@ -336,6 +358,9 @@ int mppi_set_kernel_timing(MppiHandle * h, int enabled);
 int mppi_kernel_time_ms(MppiHandle * h, int reset, double * ms_per_launch, uint64_t * launches);
 /* The stream the handle launches on (cudaStream_t), for event timing by the caller. */
 void * mppi_stream(MppiHandle * h);
+/* Launch on the caller's stream instead (e.g. the stream torch.distributed orders its NCCL
+ * collectives against); NULL restores the handle's own stream. */
+int mppi_set_stream(MppiHandle * h, void * cuda_stream);
 int mppi_device_synchronize(MppiHandle * h);
 
 /* ---- batch sharding across GPUs: one process per GPU, collectives by the caller ---- */

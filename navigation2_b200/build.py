@@ -69,8 +69,15 @@ def build_oracle(verbose: bool = False) -> None:
 
 
 def build_all(force: bool = False, verbose: bool = False) -> None:
-    build_product(force=force, verbose=verbose)
-    build_oracle(verbose=verbose)
+    # one builder at a time (torchrun starts several ranks in the same tree)
+    import fcntl
+    with open(os.path.join(ROOT, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            build_product(force=force, verbose=verbose)
+            build_oracle(verbose=verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

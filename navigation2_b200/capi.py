@@ -158,6 +158,17 @@ class MppiCycleOut(C.Structure):
     ]
 
 
+class MppiOptimizerState(C.Structure):
+    _fields_ = [
+        ("last_command_vel", C.c_double * 3),
+        ("control_history", C.c_float * 12),
+        ("cmd_history_vx", C.c_float * MPPI_MAX_DELAY_STEPS),
+        ("cmd_history_vy", C.c_float * MPPI_MAX_DELAY_STEPS),
+        ("cmd_history_wz", C.c_float * MPPI_MAX_DELAY_STEPS),
+        ("fallback_counter", C.c_uint32),
+    ]
+
+
 # every symbol include/mppi_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _F = C.POINTER(C.c_float)
@@ -172,6 +183,7 @@ SYMBOLS = {
     "mppi_sizeof_critic_params": (C.c_size_t, []),
     "mppi_sizeof_cycle_in": (C.c_size_t, []),
     "mppi_sizeof_cycle_out": (C.c_size_t, []),
+    "mppi_sizeof_optimizer_state": (C.c_size_t, []),
     "mppi_inflation_compute_cost": (C.c_uint8, [C.c_double, C.c_double, C.c_double, C.c_double]),
     "mppi_create": (C.c_int, [C.POINTER(MppiConfig), C.POINTER(_P)]),
     "mppi_destroy": (C.c_int, [_P]),
@@ -188,11 +200,14 @@ SYMBOLS = {
     "mppi_get_tensor": (C.c_int, [_P, C.c_uint32, C.c_int32, _P, C.c_size_t]),
     "mppi_get_control_sequence": (C.c_int, [_P, C.c_uint32, _F, _F, _F]),
     "mppi_set_control_sequence": (C.c_int, [_P, C.c_uint32, _F, _F, _F]),
+    "mppi_get_state": (C.c_int, [_P, C.c_uint32, C.POINTER(MppiOptimizerState)]),
+    "mppi_set_state": (C.c_int, [_P, C.c_uint32, C.POINTER(MppiOptimizerState)]),
     "mppi_enqueue_resident": (C.c_int, [_P, _P]),
     "mppi_launch_count": (C.c_uint64, [_P]),
     "mppi_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "mppi_kernel_time_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "mppi_stream": (_P, [_P]),
+    "mppi_set_stream": (C.c_int, [_P, _P]),
     "mppi_device_synchronize": (C.c_int, [_P]),
     "mppi_shard_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(_P)]),
     "mppi_shard_begin": (C.c_int, [_P, C.POINTER(MppiCycleIn)]),
@@ -237,6 +252,7 @@ def check_abi(lib: C.CDLL | None = None) -> None:
         (lib.mppi_sizeof_critic_params(), C.sizeof(MppiCriticParams), "MppiCriticParams"),
         (lib.mppi_sizeof_cycle_in(), C.sizeof(MppiCycleIn), "MppiCycleIn"),
         (lib.mppi_sizeof_cycle_out(), C.sizeof(MppiCycleOut), "MppiCycleOut"),
+        (lib.mppi_sizeof_optimizer_state(), C.sizeof(MppiOptimizerState), "MppiOptimizerState"),
     ]
     for native, here, name in pairs:
         if native != here:

@@ -74,7 +74,7 @@ struct MppiHandle
   std::vector<HostRobot> robots;
   DevStatic h_static{};
 
-  cudaStream_t stream = nullptr, side = nullptr;
+  cudaStream_t stream = nullptr, own_stream = nullptr, side = nullptr;
   cudaEvent_t map_event = nullptr;
   bool map_event_pending = false;
 
@@ -878,6 +878,7 @@ int mppi_create(const MppiConfig * cfg, MppiHandle ** out)
     h->error = "stream/event creation failed";
     return fail(MPPI_ERR_CUDA);
   }
+  h->own_stream = h->stream;
   h->robots.assign(h->R, HostRobot());
   rc = allocate(h);
   if (rc != MPPI_OK) {return fail(rc);}
@@ -905,7 +906,7 @@ int mppi_destroy(MppiHandle * h)
   if (h->h_map_stage) {cudaFreeHost(h->h_map_stage);}
   for (auto & p : h->timing_events) {cudaEventDestroy(p.first); cudaEventDestroy(p.second);}
   cudaEventDestroy(h->map_event);
-  cudaStreamDestroy(h->stream);
+  cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->side);
   delete h;
   return MPPI_OK;
@@ -1254,6 +1255,39 @@ int mppi_set_control_sequence(MppiHandle * h, uint32_t robot, const float * vx, 
   return MPPI_OK;
 }
 
+int mppi_get_state(MppiHandle * h, uint32_t robot, MppiOptimizerState * state)
+{
+  if (!h || !state || robot >= static_cast<uint32_t>(h->R)) {return MPPI_ERR_INVALID_ARGUMENT;}
+  std::memset(state, 0, sizeof(*state));
+  const HostRobot & rb = h->robots[robot];
+  state->last_command_vel[0] = rb.last_cmd_vx;
+  state->last_command_vel[1] = rb.last_cmd_vy;
+  state->last_command_vel[2] = rb.last_cmd_wz;
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  CU_CHECK(h, cudaMemcpy(state->control_history, h->d_hist + robot * 12, 12 * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < rb.hist_vx.size(); ++i) {state->cmd_history_vx[i] = rb.hist_vx[i];}
+  for (size_t i = 0; i < rb.hist_vy.size(); ++i) {state->cmd_history_vy[i] = rb.hist_vy[i];}
+  for (size_t i = 0; i < rb.hist_wz.size(); ++i) {state->cmd_history_wz[i] = rb.hist_wz[i];}
+  state->fallback_counter = static_cast<uint32_t>(rb.fallback_counter);
+  return MPPI_OK;
+}
+
+int mppi_set_state(MppiHandle * h, uint32_t robot, const MppiOptimizerState * state)
+{
+  if (!h || !state || robot >= static_cast<uint32_t>(h->R)) {return MPPI_ERR_INVALID_ARGUMENT;}
+  HostRobot & rb = h->robots[robot];
+  rb.last_cmd_vx = state->last_command_vel[0];
+  rb.last_cmd_vy = state->last_command_vel[1];
+  rb.last_cmd_wz = state->last_command_vel[2];
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  CU_CHECK(h, cudaMemcpy(h->d_hist + robot * 12, state->control_history, 12 * sizeof(float), cudaMemcpyHostToDevice));
+  for (size_t i = 0; i < rb.hist_vx.size(); ++i) {rb.hist_vx[i] = state->cmd_history_vx[i];}
+  for (size_t i = 0; i < rb.hist_vy.size(); ++i) {rb.hist_vy[i] = state->cmd_history_vy[i];}
+  for (size_t i = 0; i < rb.hist_wz.size(); ++i) {rb.hist_wz[i] = state->cmd_history_wz[i];}
+  rb.fallback_counter = state->fallback_counter;
+  return MPPI_OK;
+}
+
 int mppi_enqueue_resident(MppiHandle * h, void * cuda_stream)
 {
   if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
@@ -1295,6 +1329,14 @@ int mppi_kernel_time_ms(MppiHandle * h, int reset, double * ms_per_launch, uint6
 }
 
 void * mppi_stream(MppiHandle * h) {return h ? static_cast<void *>(h->stream) : nullptr;}
+
+int mppi_set_stream(MppiHandle * h, void * cuda_stream)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return MPPI_OK;
+}
 
 int mppi_device_synchronize(MppiHandle * h)
 {

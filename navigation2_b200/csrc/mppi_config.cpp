@@ -182,6 +182,7 @@ size_t mppi_sizeof_config(void) {return sizeof(MppiConfig);}
 size_t mppi_sizeof_critic_params(void) {return sizeof(MppiCriticParams);}
 size_t mppi_sizeof_cycle_in(void) {return sizeof(MppiCycleIn);}
 size_t mppi_sizeof_cycle_out(void) {return sizeof(MppiCycleOut);}
+size_t mppi_sizeof_optimizer_state(void) {return sizeof(MppiOptimizerState);}
 
 // nav2_costmap_2d/include/nav2_costmap_2d/inflation_layer.hpp:121-135
 uint8_t mppi_inflation_compute_cost(

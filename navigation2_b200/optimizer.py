@@ -270,6 +270,14 @@ class Optimizer(EngineBase):
                                               u[2].ctypes.data_as(fp))
         _raise_for(self._lib, self._h, rc)
 
+    def getState(self, robot: int = 0) -> capi.MppiOptimizerState:
+        st = capi.MppiOptimizerState()
+        _raise_for(self._lib, self._h, self._lib.mppi_get_state(self._h, robot, C.byref(st)))
+        return st
+
+    def setState(self, st: capi.MppiOptimizerState, robot: int = 0) -> None:
+        _raise_for(self._lib, self._h, self._lib.mppi_set_state(self._h, robot, C.byref(st)))
+
     # -- measurement -------------------------------------------------------------------------
     def enqueueResident(self, cuda_stream: int | None = None) -> None:
         _raise_for(self._lib, self._h, self._lib.mppi_enqueue_resident(self._h, cuda_stream))

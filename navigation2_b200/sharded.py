@@ -1,0 +1,90 @@
+"""Batch sharding across GPUs: one process per GPU, torch.distributed (NCCL) for the
+two small exchanges per iteration.  The trajectory axis is split evenly; costmap, path and control
+sequence are replicated; Philox noise is keyed by the global trajectory index, so the result does
+not depend on the number of ranks.
+
+  kernel A (rollout + per-trajectory critics)
+  all-reduce MAX over the 8 reduction words      furthest path point, -min repulsion, any-free flags
+  kernels B, C, D1 (path critics, local softmax partials, local (min, sum, W) slot)
+  all-gather of the (2 + 3T)-float slots          rescaled by exp(-(m_g - m)/temperature) in kernel D2
+  kernel D2 (combine, Savitzky-Golay filter, constraints, validator) — run redundantly on every rank
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .optimizer import CycleInput, CycleResult, Optimizer, _raise_for
+
+
+class _DeviceBuffer:
+    """Zero-copy view of a raw device pointer for torch.as_tensor."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class ShardedOptimizer(Optimizer):
+    def __init__(self, cfg: capi.MppiConfig, group=None):
+        import torch
+        import torch.distributed as dist
+        if cfg.n_robots != 1:
+            raise ValueError("batch sharding drives one robot; fleets are partitioned per GPU without collectives")
+        super().__init__(cfg)
+        self._torch = torch
+        self._dist = dist
+        self._group = group
+        self.world = int(cfg.shard_world)
+        self._distributed = self.world > 1
+        if self._distributed and (not dist.is_initialized() or dist.get_world_size(group) != self.world):
+            raise RuntimeError("shard_world does not match the torch.distributed world size")
+        # launch on torch's current stream so NCCL collectives are ordered against our kernels
+        stream = torch.cuda.current_stream().cuda_stream
+        _raise_for(self._lib, self._h, self._lib.mppi_set_stream(self._h, stream))
+        ar1, slot, slot_all = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n1, n2 = C.c_size_t(), C.c_size_t()
+        _raise_for(self._lib, self._h, self._lib.mppi_shard_buffers(
+            self._h, C.byref(ar1), C.byref(n1), C.byref(slot), C.byref(n2), C.byref(slot_all)))
+        self._ar1 = torch.as_tensor(_DeviceBuffer(ar1.value, n1.value, "<i4"), device="cuda")
+        self._slot = torch.as_tensor(_DeviceBuffer(slot.value, n2.value, "<f4"), device="cuda")
+        self._slot_all = torch.as_tensor(_DeviceBuffer(slot_all.value, n2.value * self.world, "<f4"), device="cuda")
+
+    def evalControl(self, inp: CycleInput, raise_on_failure: bool = True) -> CycleResult:
+        lib, h = self._lib, self._h
+        c_in = (capi.MppiCycleIn * 1)(inp.to_c())
+        c_out = (capi.MppiCycleOut * 1)()
+        T = self.T
+        u = np.zeros((3, T), dtype=np.float32)
+        traj = np.zeros((3, T), dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        c_out[0].control_vx = u[0].ctypes.data_as(fp)
+        c_out[0].control_vy = u[1].ctypes.data_as(fp)
+        c_out[0].control_wz = u[2].ctypes.data_as(fp)
+        c_out[0].optimal_trajectory = traj.ctypes.data_as(fp)
+        _raise_for(lib, h, lib.mppi_shard_begin(h, c_in))
+        iters = int(self.cfg.iteration_count)
+        while True:
+            for it in range(iters):
+                _raise_for(lib, h, lib.mppi_shard_rollout(h))
+                if self._distributed:
+                    self._dist.all_reduce(self._ar1, op=self._dist.ReduceOp.MAX, group=self._group)
+                _raise_for(lib, h, lib.mppi_shard_score(h))
+                if self._distributed:
+                    self._dist.all_gather_into_tensor(self._slot_all, self._slot, group=self._group)
+                else:
+                    self._slot_all.copy_(self._slot)
+                _raise_for(lib, h, lib.mppi_shard_update(h, 1 if it == iters - 1 else 0))
+            rc = lib.mppi_shard_end(h, c_out)
+            if rc == 1:
+                continue  # fallback(): every rank saw the same flags and retries together
+            _raise_for(lib, h, rc)
+            break
+        o = c_out[0]
+        res = CycleResult(status=o.status, cmd=(o.cmd_vx, o.cmd_vy, o.cmd_wz), control_sequence=u,
+                          optimal_trajectory=traj.T.copy(), fail_flag=bool(o.fail_flag), validation=o.validation,
+                          retries=o.retries, furthest_reached_path_point=o.furthest_reached_path_point)
+        if raise_on_failure and res.status != capi.MPPI_OK:
+            _raise_for(lib, h, res.status)
+        return res

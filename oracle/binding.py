@@ -35,6 +35,8 @@ _SYMS = {
     "oracle_get_control_sequence": (C.c_int, [_P, _F, _F, _F]),
     "oracle_set_control_sequence": (C.c_int, [_P, _F, _F, _F]),
     "oracle_last_error": (C.c_char_p, [_P]),
+    "oracle_get_state": (C.c_int, [_P, C.POINTER(capi.MppiOptimizerState)]),
+    "oracle_set_state": (C.c_int, [_P, C.POINTER(capi.MppiOptimizerState)]),
     "oracle_predict": (C.c_int, [_P, _F, _F, _F, _F, _F, _F]),
     "oracle_push_command_history": (C.c_int, [_P, C.c_float, C.c_float, C.c_float]),
     "oracle_integrate": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, _F, _F, _F, _F, _F, _F]),
@@ -215,6 +217,14 @@ class OracleOptimizer:
     def setControlSequence(self, u):
         u = np.ascontiguousarray(u, dtype=np.float32).reshape(3, self.T)
         self._lib.oracle_set_control_sequence(self._h, _p(u[0]), _p(u[1]), _p(u[2]))
+
+    def getState(self):
+        st = capi.MppiOptimizerState()
+        self._lib.oracle_get_state(self._h, C.byref(st))
+        return st
+
+    def setState(self, st):
+        self._lib.oracle_set_state(self._h, C.byref(st))
 
     # --- unit-level entry points (known-answer tests transcribed from the reference) ---
     def predict(self, state):

@@ -2214,6 +2214,44 @@ int oracle_set_control_sequence(void * h, const float * vx, const float * vy, co
   return MPPI_OK;
 }
 
+int oracle_get_state(void * h, MppiOptimizerState * state)
+{
+  auto * o = static_cast<Optimizer *>(h);
+  std::memset(state, 0, sizeof(*state));
+  state->last_command_vel[0] = o->last_command_vel_.vx;
+  state->last_command_vel[1] = o->last_command_vel_.vy;
+  state->last_command_vel[2] = o->last_command_vel_.wz;
+  for (int i = 0; i < 4; ++i) {
+    state->control_history[3 * i] = o->control_history_[i].vx;
+    state->control_history[3 * i + 1] = o->control_history_[i].vy;
+    state->control_history[3 * i + 2] = o->control_history_[i].wz;
+  }
+  const auto & m = o->motion_model_;
+  for (size_t i = 0; i < m.cmd_history_vx_.size(); ++i) {state->cmd_history_vx[i] = m.cmd_history_vx_[i];}
+  for (size_t i = 0; i < m.cmd_history_vy_.size(); ++i) {state->cmd_history_vy[i] = m.cmd_history_vy_[i];}
+  for (size_t i = 0; i < m.cmd_history_wz_.size(); ++i) {state->cmd_history_wz[i] = m.cmd_history_wz_[i];}
+  state->fallback_counter = static_cast<uint32_t>(o->fallback_counter_);
+  return MPPI_OK;
+}
+
+int oracle_set_state(void * h, const MppiOptimizerState * state)
+{
+  auto * o = static_cast<Optimizer *>(h);
+  o->last_command_vel_.vx = state->last_command_vel[0];
+  o->last_command_vel_.vy = state->last_command_vel[1];
+  o->last_command_vel_.wz = state->last_command_vel[2];
+  for (int i = 0; i < 4; ++i) {
+    o->control_history_[i] = {state->control_history[3 * i], state->control_history[3 * i + 1],
+      state->control_history[3 * i + 2]};
+  }
+  auto & m = o->motion_model_;
+  for (size_t i = 0; i < m.cmd_history_vx_.size(); ++i) {m.cmd_history_vx_[i] = state->cmd_history_vx[i];}
+  for (size_t i = 0; i < m.cmd_history_vy_.size(); ++i) {m.cmd_history_vy_[i] = state->cmd_history_vy[i];}
+  for (size_t i = 0; i < m.cmd_history_wz_.size(); ++i) {m.cmd_history_wz_[i] = state->cmd_history_wz[i];}
+  o->fallback_counter_ = state->fallback_counter;
+  return MPPI_OK;
+}
+
 const char * oracle_last_error(void * h)
 {
   return static_cast<Optimizer *>(h)->error_.c_str();

@@ -1,0 +1,135 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs with the same injected noise (BASELINE.json north_star):
+  - integer costmap indices and collision flags bit-exact,
+  - per-trajectory costs within 1e-4 relative,
+  - cmd_vel and the control sequence within 1e-5 absolute.
+"""
+import numpy as np
+import pytest
+
+from navigation2_b200 import capi, params as P, scenarios as S
+import navigation2_b200 as nb
+
+from util import ALL_CRITICS, SQUARE_FOOTPRINT, Pair, assert_costs_close, assert_cycle_close, build_map
+
+pytestmark = pytest.mark.gpu
+
+TENSORS = [("vx", capi.TENSOR_VX), ("vy", capi.TENSOR_VY), ("wz", capi.TENSOR_WZ),
+           ("cvx", capi.TENSOR_CVX), ("cvy", capi.TENSOR_CVY), ("cwz", capi.TENSOR_CWZ),
+           ("x", capi.TENSOR_X), ("y", capi.TENSOR_Y), ("yaw", capi.TENSOR_YAW)]
+
+
+def compare_state(pair, label, cells_cost=True, cells_obs=False, exact=True):
+    """exact=True: both sides started the iteration from bit-identical state, so every tensor and
+    every cell index must match bit for bit.  exact=False (second iteration of one call: the
+    control sequences already differ in the last ulp): tensors to 2e-5, cell indices may differ
+    only for the handful of samples that sit within that distance of a cell boundary."""
+    for name, which in TENSORS:
+        g = pair.gpu.getTensor(which)
+        c = pair.cpu.getTensor(which)
+        if exact:
+            # same arithmetic, same order, no FMA contraction on either side: bit-identical
+            bad = np.flatnonzero(g.view(np.uint32) != c.view(np.uint32))
+            assert bad.size == 0, f"{label} tensor {name}: {bad.size} differing elements, first at {bad[:5]}: " \
+                                  f"{g.ravel()[bad[:5]]} vs {c.ravel()[bad[:5]]}"
+        else:
+            # positions are ~10 m (float ulp 1e-6): allow a few ulps once the sequences have drifted apart
+            np.testing.assert_allclose(g, c, rtol=0, atol=2e-5, err_msg=f"{label} tensor {name}")
+    for on, which, what in ((cells_cost, capi.TENSOR_COST_CELLS, "CostCritic"),
+                            (cells_obs, capi.TENSOR_OBSTACLE_CELLS, "ObstaclesCritic")):
+        if not on:
+            continue
+        g = pair.gpu.getTensor(which)
+        c = pair.cpu.getTensor(which)
+        if exact:
+            assert np.array_equal(g, c), f"{label} {what} cell indices differ at {np.argwhere(g != c)[:5]}"
+        else:
+            assert np.count_nonzero(g != c) <= max(2, g.size // 20000), f"{label} {what} cell indices diverge"
+    if not exact:
+        return
+    g = pair.gpu.getTensor(capi.TENSOR_COLLISIONS)
+    c = pair.cpu.getTensor(capi.TENSOR_COLLISIONS)
+    assert np.array_equal(g, c), f"{label} collision flags differ"
+    assert_costs_close(pair.gpu.getTensor(capi.TENSOR_COSTS), pair.cpu.getTensor(capi.TENSOR_COSTS), label=label)
+    gc = pair.gpu.getTensor(capi.TENSOR_CRITIC_COSTS)
+    cc = pair.cpu.getTensor(capi.TENSOR_CRITIC_COSTS)
+    for k in range(gc.shape[0]):
+        assert_costs_close(gc[k], cc[k], rel=1e-4, label=f"{label} critic {k}")
+
+
+def drive(pair, path, pose, speed, cycles, label, goal_tol=0.25, resync=True, **cmp):
+    """Closed loop: integrate the commanded twist like a perfect robot so later cycles see new poses.
+    resync=True hands the oracle's carried state (control sequence, SG history, last command) to
+    the GPU after every cycle, so each cycle is an independent bit-exact comparison; resync=False
+    lets the two implementations run free and checks they stay within tolerance."""
+    x, y, yaw = pose
+    vx, vy, wz = speed
+    dt = pair.cfg.model_dt
+    for i in range(cycles):
+        inp = nb.CycleInput(pose=(x, y, yaw), speed=(vx, vy, wz), path=path, goal=tuple(path[-1]),
+                            goal_checker_xy_tolerance=goal_tol)
+        g, c = pair.step(inp)
+        assert_cycle_close(g, c, label=f"{label} cycle {i}")
+        compare_state(pair, f"{label} cycle {i}", **cmp)
+        if resync:
+            pair.gpu.setState(pair.cpu.getState())
+            pair.gpu.setControlSequence(pair.cpu.getOptimalControlSequence())
+        vx, vy, wz = c.cmd
+        x += (vx * np.cos(yaw) - vy * np.sin(yaw)) * dt
+        y += (vx * np.sin(yaw) + vy * np.cos(yaw)) * dt
+        yaw += wz * dt
+
+
+def test_c1_diffdrive_default_critics_injected_noise():
+    """BASELINE.json configs[1]: DiffDrive 2000x56, default critics (yaml weights), 400x400 @0.05 m."""
+    cfg = P.nav2_bringup_config(materialize_tensors=1, visualize=1, debug_cells=1)
+    cells = build_map("blocks", seed=1)
+    pair = Pair(cfg, cells)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    drive(pair, path, (10.0, 10.0, 0.0), (0.2, 0.0, 0.0), cycles=12, label="C1")
+    pair.close()
+
+
+def test_c1_two_iterations_reference_fixture():
+    """The reference harness's own fixture: 40x40 @0.1 m, 8x8 block of cost 250, iteration_count 2
+    (benchmark/optimizer_benchmark.cpp:49-99)."""
+    cells, res, origin, path = S.reference_benchmark_fixture()
+    cfg = P.make_config(
+        {"batch_size": 2000, "time_steps": 56, "iteration_count": 2, "motion_model": "diff_drive",
+         "materialize_tensors": 1, "visualize": 1, "debug_cells": 1},
+        P.NAV2_BRINGUP_CRITICS, robot_radius=0.15)
+    pair = Pair(cfg, cells, resolution=res, origin=origin)
+    drive(pair, path, (2.0, 2.0, 0.785), (0.0, 0.0, 0.0), cycles=6, label="fixture-2iter", exact=False)
+    pair.close()
+
+
+def test_c1_free_running_stays_within_tolerance():
+    """No resynchronisation for 30 cycles: ulp-level differences in the softmax sums must not grow."""
+    cfg = P.nav2_bringup_config(materialize_tensors=1, visualize=1, debug_cells=1)
+    cells = build_map("blocks", seed=2)
+    pair = Pair(cfg, cells)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    drive(pair, path, (10.0, 10.0, 0.0), (0.0, 0.0, 0.0), cycles=30, label="free", resync=False, exact=False)
+    pair.close()
+
+
+@pytest.mark.parametrize("model", ["omni", "ackermann"])
+@pytest.mark.parametrize("footprint", [False, True])
+def test_c3_models_full_critics(model, footprint):
+    """BASELINE.json configs[2] at a size the oracle finishes in seconds: Omni / Ackermann, the full
+    critic set incl. ObstaclesCritic + inflation, point and footprint collision checking."""
+    overrides = {"CostCritic": {"consider_footprint": footprint}, "ObstaclesCritic": {"consider_footprint": footprint},
+                 "VelocityDeadbandCritic": {"deadband_velocities": [0.05, 0.05, 0.05]}}
+    kw = dict(footprint=SQUARE_FOOTPRINT) if footprint else dict(robot_radius=0.22)
+    cfg = P.make_config(
+        {"batch_size": 1024, "time_steps": 100, "motion_model": model, "materialize_tensors": 1, "visualize": 1,
+         "debug_cells": 1, "controller_frequency": 20.0},
+        ALL_CRITICS, overrides, inflation={"cost_scaling_factor": 3.0, "inflation_radius": 0.70},
+        validator={"consider_footprint": footprint}, **kw)
+    inscribed = cfg.inscribed_radius
+    cells = build_map("blocks", seed=3, inscribed=inscribed, n_blocks=40, clear_radius=0.6)
+    pair = Pair(cfg, cells)
+    path = S.arc_path((10.0, 10.0, 0.3), n_points=120, curvature=-0.2)
+    drive(pair, path, (10.0, 10.0, 0.3), (0.1, 0.0, 0.0), cycles=5, label=f"C3-{model}-fp{footprint}",
+          cells_obs=True)
+    pair.close()
