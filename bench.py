@@ -278,7 +278,10 @@ def run_ours(args):
 
     opt = setup_engine(wl, seed=42 + 1000 * rank)
     inputs = wl["inp"] if R == 1 else [wl["inp"]] * R
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library treats a NULL stream argument as "use my own", and
+    # CUDA events only see the stream they are recorded on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # 256 MiB > 126 MB L2
 
     # first call through the public API: uploads the cycle inputs that the resident path replays

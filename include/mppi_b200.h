@@ -192,6 +192,10 @@ typedef struct MppiCycleIn
   double goal_x, goal_y, goal_yaw;          /* `goal` argument (kept for CriticData::goal parity) */
   int32_t has_goal_checker;                 /* goal_checker != nullptr */
   double goal_checker_xy_tolerance;         /* pose_tolerance.position.x from GoalChecker::getTolerances */
+  /* models::State::local_path_length is normally calculate_path_length(plan) (optimizer.cpp:333).  The
+   * reference's critic tests write the field directly; set has_local_path_length to do the same. */
+  int32_t has_local_path_length;
+  double local_path_length;
 } MppiCycleIn;
 
 typedef enum MppiValidation

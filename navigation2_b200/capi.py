@@ -140,6 +140,8 @@ class MppiCycleIn(C.Structure):
         ("goal_x", C.c_double), ("goal_y", C.c_double), ("goal_yaw", C.c_double),
         ("has_goal_checker", C.c_int32),
         ("goal_checker_xy_tolerance", C.c_double),
+        ("has_local_path_length", C.c_int32),
+        ("local_path_length", C.c_double),
     ]
 
 

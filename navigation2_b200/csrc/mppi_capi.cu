@@ -546,6 +546,7 @@ int prepare_robot(MppiHandle * h, int r, const MppiCycleIn & in, int preset_furt
       path_length += std::hypot(in.path_x[i] - in.path_x[i + 1], in.path_y[i] - in.path_y[i + 1]);
     }
   }
+  if (in.has_local_path_length) {path_length = in.local_path_length;}
   cy.local_path_length = static_cast<float>(path_length);
   const int n = static_cast<int>(in.n_path);
   cy.n_path = n;
@@ -710,7 +711,10 @@ KArgs make_args(MppiHandle * h)
 struct LaunchPlan
 {
   KSmemA sm_a;
+  KSmemA sm_tensors;  // score_tensors: no noise ring
+  KPlanA ka;
   int block_a;
+  int block_b;
   int path_cap;
 };
 
@@ -732,7 +736,34 @@ LaunchPlan make_plan(MppiHandle * h)
         h->holo ? std::max(h->off_vy, 1) - 1 : 0});
   const int ring = lag > 0 ? lag + 1 : 0;
   const bool obstacles = h->critic_of_type[MPPI_CRITIC_OBSTACLES] >= 0;
-  p.sm_a = mppi_smem_layout_a(h->T, need ? p.path_cap : 0, obstacles, ring, p.block_a, win_bytes);
+  // noise ring: every time-step chunk in flight if it fits in ~40 KB, else a 4-deep ring.
+  // Bulk copies need 16-byte aligned column segments: B % 4 == 0 (blocks start at multiples of 64).
+  const int axes = h->holo ? 3 : 2;
+  const int n_chunks = (h->T + MPPI_TCHUNK_A - 1) / MPPI_TCHUNK_A;
+  const size_t stage_bytes = sizeof(float) * axes * MPPI_TCHUNK_A * p.block_a;
+  int stages = static_cast<int>(std::min<size_t>(n_chunks, std::max<size_t>(2, (40 * 1024) / stage_bytes)));
+  stages = std::min(stages, MPPI_MAX_STAGES);
+  if (h->B % 4 != 0) {stages = 0;}
+  p.sm_a = mppi_smem_layout_a(h->T, need ? p.path_cap : 0, obstacles, ring, p.block_a, win_bytes, axes, stages);
+  p.sm_tensors = mppi_smem_layout_a(h->T, need ? p.path_cap : 0, obstacles, 0, p.block_a, win_bytes, axes, 0);
+  p.block_b = 128;
+  // kernel instantiation: union of the active critics' types over the robots of this call
+  uint32_t types = 0;
+  for (int r = 0; r < h->R; ++r) {
+    const DevCycle & cy = *h->hcyc(r);
+    if (!cy.run) {continue;}
+    for (uint32_t k = 0; k < h->cfg.n_critics; ++k) {
+      if ((cy.active_mask >> k) & 1u) {types |= 1u << h->cfg.critics[k].type;}
+    }
+  }
+  p.ka.block = p.block_a;
+  p.ka.holo = h->holo;
+  p.ka.from_tensors = false;
+  p.ka.full = h->cfg.materialize_tensors || h->cfg.debug_cells || h->cfg.visualize || h->cfg.clamp_raw_controls || lag > 0;
+  p.ka.crit_types = types;
+  const int kc = h->critic_of_type[MPPI_CRITIC_COST], kp = h->critic_of_type[MPPI_CRITIC_PATH_ALIGN];
+  p.ka.cc_step = kc >= 0 ? static_cast<int>(h->cfg.critics[kc].trajectory_point_step) : 2;
+  p.ka.pa_step = kp >= 0 ? static_cast<int>(h->cfg.critics[kp].trajectory_point_step) : 4;
   return p;
 }
 
@@ -755,9 +786,9 @@ int enqueue_iterations(MppiHandle * h, cudaStream_t stream, const LaunchPlan & p
       h->timing_used++;
       CU_CHECK(h, cudaEventRecord(e0, stream));
     }
-    CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, h->holo, false, plan.block_a, stream));
+    CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, plan.ka, stream));
     if (h->timing) {CU_CHECK(h, cudaEventRecord(e1, stream));}
-    CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, false, plan.block_a, stream));
+    CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, false, plan.block_b, stream));
     CU_CHECK(h, mppi_launch_softmax_partial(a, h->holo, stream));
     CU_CHECK(h, mppi_launch_finalize(a, h->holo, 0, stream));
     h->launches += 4;
@@ -1166,8 +1197,10 @@ int mppi_score_tensors(
   rc = wait_map(h, h->stream);
   if (rc != MPPI_OK) {return rc;}
   KArgs a = make_args(h);
-  CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, h->holo, true, plan.block_a, h->stream));
-  CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, true, plan.block_a, h->stream));
+  KPlanA ka = plan.ka;
+  ka.from_tensors = true;
+  CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_tensors, ka, h->stream));
+  CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, true, plan.block_b, h->stream));
   h->launches += 2;
   CU_CHECK(h, cudaMemcpyAsync(costs, h->d_costs + static_cast<size_t>(robot) * h->B, sizeof(float) * h->B, cudaMemcpyDeviceToHost, h->stream));
   if (collisions) {
@@ -1382,7 +1415,7 @@ int mppi_shard_rollout(MppiHandle * h)
   if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
   const LaunchPlan plan = make_plan(h);
   KArgs a = make_args(h);
-  CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, h->holo, false, plan.block_a, h->stream));
+  CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, plan.ka, h->stream));
   h->launches += 1;
   return MPPI_OK;
 }
@@ -1392,7 +1425,7 @@ int mppi_shard_score(MppiHandle * h)
   if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
   const LaunchPlan plan = make_plan(h);
   KArgs a = make_args(h);
-  CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, false, plan.block_a, h->stream));
+  CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, false, plan.block_b, h->stream));
   CU_CHECK(h, mppi_launch_softmax_partial(a, h->holo, h->stream));
   CU_CHECK(h, mppi_launch_finalize(a, h->holo, 1, h->stream));
   h->launches += 3;

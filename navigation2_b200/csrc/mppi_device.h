@@ -10,9 +10,11 @@
 #include "mppi_b200.h"
 
 #define MPPI_MAX_PATH_POINTS 2048
-#define MPPI_BLOCK_A 128        // rollout+score kernel: threads per block (one trajectory each)
+#define MPPI_BLOCK_A 256        // rollout+score kernel, throughput mode: threads per block (one trajectory each)
 #define MPPI_BLOCK_C 256        // softmax partial kernel
 #define MPPI_TCHUNK 8           // time steps reduced together in the softmax partial kernel
+#define MPPI_TCHUNK_A 8         // time steps per bulk-async stage of the rollout kernel
+#define MPPI_MAX_STAGES 16      // ring slots (mbarriers) of the rollout kernel's noise pipeline
 #define MPPI_MAX_PARTIAL_BLOCKS 296  // 2 x 148 SMs
 
 // slots of the per-robot reduction words (int32); the first MPPI_AR1_WORDS are what batch

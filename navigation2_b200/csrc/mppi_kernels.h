@@ -15,6 +15,8 @@ struct KSmemA
   uint32_t off_lut;    // float obstacle distance LUT [2][256]
   uint32_t off_ring;   // float delay ring [3][ring_depth][block]
   uint32_t off_win;    // uint8 costmap window
+  uint32_t off_noise;  // float noise ring [noise_stages][axes][MPPI_TCHUNK_A][block], filled by cp.async.bulk
+  int32_t noise_stages;  // 0 = read noise straight from global memory
   int32_t path_cap;
   int32_t ring_depth;
   uint32_t total;
@@ -26,10 +28,22 @@ struct KSmemB
   uint32_t total;
 };
 
-KSmemA mppi_smem_layout_a(int T, int path_cap, bool obstacles, int ring_depth, int block, int win_bytes);
+KSmemA mppi_smem_layout_a(
+  int T, int path_cap, bool obstacles, int ring_depth, int block, int win_bytes, int noise_axes, int noise_stages);
+
+// what the host knows about this launch; selects the kernel instantiation
+struct KPlanA
+{
+  int block;             // 64 (latency mode, small batches) or MPPI_BLOCK_A
+  bool holo;
+  bool from_tensors;     // score_tensors: state / trajectories come from caller tensors
+  bool full;             // materialize / debug cells / collision flags / clamp_raw_controls / input delay
+  uint32_t crit_types;   // union of CRIT bits (1 << MppiCriticType) of the critics active this call
+  int cc_step, pa_step;  // trajectory_point_step of CostCritic / PathAlignCritic (0 if absent)
+};
 
 cudaError_t mppi_launch_rollout_score(
-  const KArgs & a, const KSmemA & sm, bool holo, bool from_tensors, int block, cudaStream_t stream);
+  const KArgs & a, const KSmemA & sm, const KPlanA & plan, cudaStream_t stream);
 cudaError_t mppi_launch_path_score(
   const KArgs & a, int path_cap, bool holo, bool from_tensors, int block, cudaStream_t stream);
 cudaError_t mppi_launch_softmax_partial(const KArgs & a, bool holo, cudaStream_t stream);

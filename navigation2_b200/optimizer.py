@@ -50,6 +50,7 @@ class CycleInput:
     path: np.ndarray                              # plan: (n, 3) float64 x, y, yaw
     goal: tuple[float, float, float] = (0.0, 0.0, 0.0)
     goal_checker_xy_tolerance: float | None = None  # None = goal_checker == nullptr
+    local_path_length: float | None = None          # None = calculate_path_length(plan)
     _keep: list = field(default_factory=list, repr=False)
 
     def to_c(self) -> capi.MppiCycleIn:
@@ -66,6 +67,8 @@ class CycleInput:
         c.goal_x, c.goal_y, c.goal_yaw = (float(v) for v in self.goal)
         c.has_goal_checker = 0 if self.goal_checker_xy_tolerance is None else 1
         c.goal_checker_xy_tolerance = float(self.goal_checker_xy_tolerance or 0.0)
+        c.has_local_path_length = 0 if self.local_path_length is None else 1
+        c.local_path_length = float(self.local_path_length or 0.0)
         return c
 
 

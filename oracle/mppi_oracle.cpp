@@ -1615,6 +1615,7 @@ struct Optimizer
         path_length += std::hypot(in.path_x[idx] - in.path_x[idx + 1], in.path_y[idx] - in.path_y[idx + 1]);
       }
     }
+    if (in.has_local_path_length) {path_length = in.local_path_length;}
     state_.local_path_length = path_length;
     // utils::toTensor utils.hpp:208-220
     path_.reset(in.n_path);
