@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -105,6 +106,9 @@ struct MppiHandle
   uint8_t * h_map_stage = nullptr;
   size_t map_stage_bytes = 0;
 
+  bool allow_fused = true;     // MPPI_B200_NO_FUSED=1 forces the general four-kernel path
+  uint64_t fused_checked_key = ~0ull;
+  bool fused_checked_ok = false;
   bool have_cycle = false;     // a cycle block is resident (mppi_enqueue_resident allowed)
   bool from_tensors_loaded = false;
   uint64_t launches = 0;
@@ -716,6 +720,9 @@ struct LaunchPlan
   int block_a;
   int block_b;
   int path_cap;
+  bool fused;          // one-cluster-per-robot single-launch path (small batches, lean configuration)
+  KSmemF sm_f;
+  int cluster_size;
 };
 
 LaunchPlan make_plan(MppiHandle * h)
@@ -764,6 +771,23 @@ LaunchPlan make_plan(MppiHandle * h)
   const int kc = h->critic_of_type[MPPI_CRITIC_COST], kp = h->critic_of_type[MPPI_CRITIC_PATH_ALIGN];
   p.ka.cc_step = kc >= 0 ? static_cast<int>(h->cfg.critics[kc].trajectory_point_step) : 2;
   p.ka.pa_step = kp >= 0 ? static_cast<int>(h->cfg.critics[kp].trajectory_point_step) : 4;
+  // fused path: the whole batch of a robot fits one thread-block cluster and nothing asks for the
+  // full-feature kernels (tensor materialisation, debug dumps, visualisation, clamp_raw, input delay)
+  p.fused = false;
+  if (h->allow_fused && h->cfg.shard_world == 1 && !p.ka.full && h->B <= MPPI_FUSED_G * MPPI_FUSED_MAX_CLUSTER) {
+    int cs = 1;
+    while (cs * MPPI_FUSED_G < h->B) {cs *= 2;}
+    p.cluster_size = cs;
+    p.sm_f = mppi_smem_layout_f(h->T, h->holo, p.path_cap, static_cast<int>(h->cfg.n_critics) + 3, obstacles, win_bytes);
+    if (p.sm_f.total <= 227u * 1024u) {
+      const uint64_t key = (static_cast<uint64_t>(p.sm_f.total) << 8) | static_cast<uint64_t>(cs);
+      if (h->fused_checked_key != key) {
+        h->fused_checked_key = key;
+        h->fused_checked_ok = mppi_fused_supported(p.sm_f, h->holo, cs);
+      }
+      p.fused = h->fused_checked_ok;
+    }
+  }
   return p;
 }
 
@@ -785,6 +809,12 @@ int enqueue_iterations(MppiHandle * h, cudaStream_t stream, const LaunchPlan & p
       e1 = h->timing_events[h->timing_used].second;
       h->timing_used++;
       CU_CHECK(h, cudaEventRecord(e0, stream));
+    }
+    if (plan.fused) {
+      CU_CHECK(h, mppi_launch_fused(a, plan.sm_f, h->holo, plan.cluster_size, stream));
+      if (h->timing) {CU_CHECK(h, cudaEventRecord(e1, stream));}
+      h->launches += 1;
+      continue;
     }
     CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, plan.ka, stream));
     if (h->timing) {CU_CHECK(h, cudaEventRecord(e1, stream));}
@@ -910,6 +940,10 @@ int mppi_create(const MppiConfig * cfg, MppiHandle ** out)
     return fail(MPPI_ERR_CUDA);
   }
   h->own_stream = h->stream;
+  {
+    const char * e = std::getenv("MPPI_B200_NO_FUSED");
+    h->allow_fused = !(e && e[0] == '1');
+  }
   h->robots.assign(h->R, HostRobot());
   rc = allocate(h);
   if (rc != MPPI_OK) {return fail(rc);}

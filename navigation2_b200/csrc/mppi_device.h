@@ -16,6 +16,9 @@
 #define MPPI_TCHUNK_A 8         // time steps per bulk-async stage of the rollout kernel
 #define MPPI_MAX_STAGES 16      // ring slots (mbarriers) of the rollout kernel's noise pipeline
 #define MPPI_MAX_PARTIAL_BLOCKS 296  // 2 x 148 SMs
+#define MPPI_FUSED_G 128        // fused small-batch kernel: trajectories per CTA
+#define MPPI_FUSED_THREADS 512  // 4 roles x MPPI_FUSED_G
+#define MPPI_FUSED_MAX_CLUSTER 16
 
 // slots of the per-robot reduction words (int32); the first MPPI_AR1_WORDS are what batch
 // sharding all-reduces with MAX across ranks

@@ -28,6 +28,26 @@ struct KSmemB
   uint32_t total;
 };
 
+// dynamic shared-memory layout of the fused one-cluster-per-robot kernel (byte offsets)
+struct KSmemF
+{
+  uint32_t off_arr;    // float [5 or 6][T][MPPI_FUSED_G]: vx, wz, yaw, x, y (, vy)
+  uint32_t off_u;      // float u[3][T]
+  uint32_t off_path;   // float path x / y / yaw / integrated distance + uint8 validity, path_cap each
+  uint32_t off_terms;  // float [n_terms + 2][MPPI_FUSED_G]
+  uint32_t off_w;      // float softmax weights [MPPI_FUSED_G]
+  uint32_t off_xch;    // FusedExchange + float W[3][T]: read by the other CTAs through DSMEM
+  uint32_t off_lut;    // float obstacle distance LUT [2][256]
+  uint32_t off_fin;    // finalize scratch, 11 T floats
+  uint32_t off_win;    // uint8 costmap window
+  int32_t path_cap;
+  uint32_t total;
+};
+
+KSmemF mppi_smem_layout_f(int T, bool holo, int path_cap, int n_terms, bool obstacles, int win_bytes);
+cudaError_t mppi_launch_fused(const KArgs & a, const KSmemF & sm, bool holo, int cluster_size, cudaStream_t stream);
+bool mppi_fused_supported(const KSmemF & sm, bool holo, int cluster_size);
+
 KSmemA mppi_smem_layout_a(
   int T, int path_cap, bool obstacles, int ring_depth, int block, int win_bytes, int noise_axes, int noise_stages);
 

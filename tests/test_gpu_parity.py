@@ -133,3 +133,68 @@ def test_c3_models_full_critics(model, footprint):
     drive(pair, path, (10.0, 10.0, 0.3), (0.1, 0.0, 0.0), cycles=5, label=f"C3-{model}-fp{footprint}",
           cells_obs=True)
     pair.close()
+
+
+def _lean_pair_check(cfg, cells, path, pose, speed, cycles, label, resolution=0.05):
+    """Lean configuration (no materialised tensors / debug dumps): this is what production runs and
+    what selects the fused one-cluster-per-robot kernel for batches <= 2048.  With resync every
+    cycle starts bit-identical, so costs must agree to 1e-4 relative and controls to 1e-5."""
+    pair = Pair(cfg, cells, resolution=resolution)
+    x, y, yaw = pose
+    vx, vy, wz = speed
+    for i in range(cycles):
+        goal = tuple(path[-1]) if len(path) else (0.0, 0.0, 0.0)
+        inp = nb.CycleInput(pose=(x, y, yaw), speed=(vx, vy, wz), path=path, goal=goal,
+                            goal_checker_xy_tolerance=0.25)
+        g, c = pair.step(inp)
+        assert_cycle_close(g, c, label=f"{label} cycle {i}")
+        assert_costs_close(pair.gpu.getTensor(capi.TENSOR_COSTS), pair.cpu.getTensor(capi.TENSOR_COSTS),
+                           label=f"{label} cycle {i}")
+        gw, cw = pair.gpu.getTensor(capi.TENSOR_SOFTMAX), pair.cpu.getTensor(capi.TENSOR_SOFTMAX)
+        np.testing.assert_allclose(gw, cw, rtol=2e-4, atol=1e-7, err_msg=f"{label} softmax weights")
+        pair.gpu.setState(pair.cpu.getState())
+        pair.gpu.setControlSequence(pair.cpu.getOptimalControlSequence())
+        vx, vy, wz = c.cmd
+        dt = cfg.model_dt
+        x += (vx * np.cos(yaw) - vy * np.sin(yaw)) * dt
+        y += (vx * np.sin(yaw) + vy * np.cos(yaw)) * dt
+        yaw += wz * dt
+    launches = pair.gpu.launchCount()
+    pair.close()
+    return launches
+
+
+def test_c1_lean_fused_cluster_kernel():
+    """BASELINE.json configs[1] exactly as benchmarked: one launch per optimize() iteration."""
+    cfg = P.nav2_bringup_config()
+    cells = build_map("blocks", seed=1)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    launches = _lean_pair_check(cfg, cells, path, (10.0, 10.0, 0.0), (0.2, 0.0, 0.0), 15, "C1-lean")
+    assert launches <= 1 + 15 + 2, f"expected the fused single-launch path, saw {launches} launches"
+
+
+@pytest.mark.parametrize("model", ["omni", "ackermann"])
+@pytest.mark.parametrize("footprint", [False, True])
+@pytest.mark.parametrize("batch", [1000, 2048, 4096])
+def test_lean_models_full_critics(model, footprint, batch):
+    """Full critic set, lean configuration: fused kernel up to 2048 trajectories, general path above."""
+    overrides = {"CostCritic": {"consider_footprint": footprint}, "ObstaclesCritic": {"consider_footprint": footprint},
+                 "VelocityDeadbandCritic": {"deadband_velocities": [0.05, 0.05, 0.05]}}
+    kw = dict(footprint=SQUARE_FOOTPRINT) if footprint else dict(robot_radius=0.22)
+    cfg = P.make_config({"batch_size": batch, "time_steps": 60, "motion_model": model, "controller_frequency": 20.0,
+                         "iteration_count": 2},
+                        ALL_CRITICS, overrides, inflation={"cost_scaling_factor": 3.0, "inflation_radius": 0.70},
+                        validator={"consider_footprint": footprint}, **kw)
+    cells = build_map("blocks", seed=3, inscribed=cfg.inscribed_radius, n_blocks=40, clear_radius=0.6)
+    path = S.arc_path((10.0, 10.0, 0.3), n_points=120, curvature=-0.2)
+    _lean_pair_check(cfg, cells, path, (10.0, 10.0, 0.3), (0.1, 0.0, 0.0), 4, f"lean-{model}-fp{footprint}-B{batch}")
+
+
+def test_near_goal_and_empty_path_lean():
+    """Goal / GoalAngle active (path shorter than their thresholds), then an empty plan (SURVEY.md §9 hazard)."""
+    cfg = P.nav2_bringup_config()
+    cells = build_map("blocks", seed=4)
+    short = S.arc_path((10.0, 10.0, 0.0), n_points=8)            # 0.35 m: Goal + GoalAngle on, path critics off
+    _lean_pair_check(cfg, cells, short, (10.0, 10.0, 0.2), (0.1, 0.0, 0.0), 3, "near-goal")
+    empty = np.zeros((0, 3))
+    _lean_pair_check(cfg, cells, empty, (10.0, 10.0, 0.2), (0.1, 0.0, 0.0), 2, "empty-path")
