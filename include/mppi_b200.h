@@ -236,7 +236,9 @@ typedef enum MppiTensor
   MPPI_TENSOR_COLLISIONS = 14,      /* uint8[B]: CriticData::trajectories_in_collision */
   MPPI_TENSOR_COST_CELLS = 15,      /* uint32[n_s * B]: CostCritic cell index per strided sample, 0xFFFFFFFF off-map, 0xFFFFFFFE not visited (debug_cells) */
   MPPI_TENSOR_OBSTACLE_CELLS = 16,  /* uint32[T * B]: ObstaclesCritic cell index per step, same sentinels (debug_cells) */
-  MPPI_TENSOR_SOFTMAX = 17          /* float[B]: unnormalised softmax weights exp(-(c - min)/temperature) */
+  MPPI_TENSOR_SOFTMAX = 17,         /* float[B]: unnormalised softmax weights exp(-(c - min)/temperature) */
+  MPPI_TENSOR_PHASE_CLOCKS = 18     /* int64[16 * 32]: SM clock at the phase boundaries of the fused kernel, per cluster rank
+                                       (tracing; enabled by the environment variable MPPI_B200_PHASE_CLOCKS=1) */
 } MppiTensor;
 
 /*

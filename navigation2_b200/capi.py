@@ -52,6 +52,7 @@ TENSOR_COLLISIONS = 14
 TENSOR_COST_CELLS = 15
 TENSOR_OBSTACLE_CELLS = 16
 TENSOR_SOFTMAX = 17
+TENSOR_PHASE_CLOCKS = 18
 
 
 class MppiCriticParams(C.Structure):

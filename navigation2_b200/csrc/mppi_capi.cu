@@ -90,6 +90,7 @@ struct MppiHandle
   uint8_t * d_collisions = nullptr;
   uint32_t * d_dbg_cost = nullptr, * d_dbg_obs = nullptr;
   int32_t * d_red = nullptr;
+  long long * d_phase_clocks = nullptr;
   float * d_partials = nullptr, * d_slot = nullptr, * d_slot_all = nullptr;
   uint8_t * d_map = nullptr;
   size_t map_stride = 0;
@@ -137,7 +138,7 @@ void free_device(MppiHandle * h)
   F(h->d_u); F(h->d_u_saved); F(h->d_hist); F(h->d_hist_saved); F(h->d_terms); F(h->d_obs_raw);
   F(h->d_obs_rep); F(h->d_last); F(h->d_pa); F(h->d_costs); F(h->d_softmax); F(h->d_critic_costs);
   F(h->d_collisions); F(h->d_dbg_cost); F(h->d_dbg_obs); F(h->d_red); F(h->d_partials); F(h->d_slot);
-  F(h->d_slot_all); F(h->d_static); F(h->d_cycle_block); F(h->d_cycle_saved); F(h->d_out);
+  F(h->d_phase_clocks); F(h->d_slot_all); F(h->d_static); F(h->d_cycle_block); F(h->d_cycle_saved); F(h->d_out);
   if (h->h_cycle_block) {cudaFreeHost(h->h_cycle_block); h->h_cycle_block = nullptr;}
   if (h->h_out) {cudaFreeHost(h->h_out); h->h_out = nullptr;}
 }
@@ -406,6 +407,10 @@ int allocate(MppiHandle * h)
       CU_CHECK(h, cudaMalloc(&h->d_dbg_obs, bt * sizeof(uint32_t)));
       CU_CHECK(h, cudaMemset(h->d_dbg_obs, 0xFF, bt * sizeof(uint32_t)));
     }
+  }
+  if (const char * e = std::getenv("MPPI_B200_PHASE_CLOCKS"); e && e[0] == '1') {
+    CU_CHECK(h, cudaMalloc(&h->d_phase_clocks, R * MPPI_FUSED_MAX_CLUSTER * 32 * sizeof(long long)));
+    CU_CHECK(h, cudaMemset(h->d_phase_clocks, 0, R * MPPI_FUSED_MAX_CLUSTER * 32 * sizeof(long long)));
   }
   CU_CHECK(h, cudaMalloc(&h->d_red, R * RED_WORDS * sizeof(int32_t)));
   {
@@ -708,6 +713,7 @@ KArgs make_args(MppiHandle * h)
   a.path_valid = h->d_cycle_block + sizeof(DevCycle) * h->R + sizeof(float) * 4 * h->max_path * h->R;
   a.cyc = reinterpret_cast<DevCycle *>(h->d_cycle_block);
   a.st = h->d_static;
+  a.phase_clocks = h->d_phase_clocks;
   a.out = h->d_out; a.out_stride = h->out_stride;
   return a;
 }
@@ -1289,6 +1295,10 @@ int mppi_get_tensor(MppiHandle * h, uint32_t robot, int32_t which, void * dst, s
       src = h->d_dbg_cost + static_cast<size_t>(h->cc_ns) * B * robot; bytes = static_cast<size_t>(h->cc_ns) * B * 4; break;
     case MPPI_TENSOR_OBSTACLE_CELLS:
       rc = need(h->d_dbg_obs, "obstacle cells"); src = h->d_dbg_obs + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_PHASE_CLOCKS:
+      rc = need(h->d_phase_clocks, "phase clocks (set MPPI_B200_PHASE_CLOCKS=1)");
+      src = h->d_phase_clocks + static_cast<size_t>(robot) * MPPI_FUSED_MAX_CLUSTER * 32;
+      bytes = MPPI_FUSED_MAX_CLUSTER * 32 * sizeof(long long); break;
     default: h->error = "unknown tensor"; return MPPI_ERR_INVALID_ARGUMENT;
   }
   if (rc != MPPI_OK) {return rc;}

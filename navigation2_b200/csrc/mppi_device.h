@@ -181,6 +181,7 @@ struct KArgs
   const uint8_t * path_valid;  // [R][max_path]
   DevCycle * cyc;       // [R]
   const DevStatic * st;
+  long long * phase_clocks;  // [R][MPPI_FUSED_MAX_CLUSTER][32] SM clock at each phase boundary of the fused kernel, or null
   uint8_t * out;        // [R][out_stride]
   size_t out_stride;
 };
