@@ -356,6 +356,15 @@ int mppi_set_state(MppiHandle * h, uint32_t robot, const MppiOptimizerState * st
  * no H2D, no D2H, no host sync.  The control sequence is restored first so every call does
  * identical work. */
 int mppi_enqueue_resident(MppiHandle * h, void * cuda_stream);
+/* mppi_enqueue_resident replays the inputs of the last mppi_optimize; keeping the pristine copies it
+ * needs costs three small device copies per cycle, so it is opt-in. */
+int mppi_set_resident_capture(MppiHandle * h, int enabled);
+/* `cycles` back-to-back (mppi_upload_costmap for every robot; mppi_optimize) pairs, each timed with
+ * steady_clock on the calling thread: the end-to-end latency of this C ABI with host buffers
+ * (H2D costmap + cycle inputs, kernels, D2H result).  per_call_seconds receives `cycles` entries. */
+int mppi_time_e2e(
+  MppiHandle * h, const uint8_t * cells, uint32_t size_x, uint32_t size_y, double resolution, double origin_x,
+  double origin_y, const MppiCycleIn * in, MppiCycleOut * out, int cycles, double * per_call_seconds);
 /* Kernels launched by this handle since creation (bench.py "gpu_launches"). */
 uint64_t mppi_launch_count(const MppiHandle * h);
 /* CUDA-event time of the dominant (rollout+score) kernel, averaged since the last call with

@@ -62,6 +62,35 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST = os.path.join(ROOT, "navigation2_b200", "host")
+HOST_LIB = os.path.join(ROOT, "navigation2_b200", "libmppi_controller_b200.so")
+HOST_TEST = os.path.join(HOST, "test_host")
+
+
+def build_host(force: bool = False, verbose: bool = False) -> str:
+    """The C++ host mirror of the reference's plugin classes (navigation2_b200/host) on top of the C ABI,
+    and its test driver.  Built against the in-tree ROS type shim; with a ROS 2 underlay it is built by colcon."""
+    src = os.path.join(HOST, "src", "mppi.cpp")
+    hdrs = [os.path.join(HOST, "include", "nav2_mppi_controller_b200", "mppi.hpp"),
+            os.path.join(HOST, "include", "ros_shim", "ros_shim.hpp"), os.path.join(ROOT, "include", "mppi_b200.h")]
+    test_src = os.path.join(HOST, "test", "test_host.cpp")
+    inc = ["-I", os.path.join(HOST, "include"), "-I", os.path.join(ROOT, "include")]
+    common = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-fPIC", *inc]
+    link = ["-L", os.path.dirname(LIB), "-lmppi_b200", "-Wl,-rpath,$ORIGIN"]
+    if force or _stale(HOST_LIB, [src, LIB, *hdrs]):
+        cmd = [*common, "-shared", src, *link, "-o", HOST_LIB]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True, cwd=ROOT)
+    if force or _stale(HOST_TEST, [test_src, HOST_LIB, *hdrs]):
+        cmd = [*common, test_src, "-L", os.path.dirname(LIB), "-lmppi_controller_b200", "-lmppi_b200",
+               "-Wl,-rpath,$ORIGIN/..", "-o", HOST_TEST]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True, cwd=ROOT)
+    return HOST_LIB
+
+
 def build_oracle(verbose: bool = False) -> None:
     """Builds the checker (oracle/) and, when /root/reference exists, oracle/_ref from the reference's own header."""
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "all"], check=True,
@@ -75,6 +104,7 @@ def build_all(force: bool = False, verbose: bool = False) -> None:
         fcntl.flock(lock, fcntl.LOCK_EX)
         try:
             build_product(force=force, verbose=verbose)
+            build_host(force=force, verbose=verbose)
             build_oracle(verbose=verbose)
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -39,7 +40,8 @@ struct HostRobot
   bool map_valid = false;
   uint32_t size_x = 0, size_y = 0, pitch = 0;
   double resolution = 0, origin_x = 0, origin_y = 0;
-  std::vector<uint8_t> map_host;  // tight copy (path validity is evaluated on the host, O(n_path))
+  const uint8_t * map_host = nullptr;  // the robot's slab of the pinned staging buffer (tight rows); path
+                                       // validity is evaluated on the host from it, O(n_path) lookups
   bool noise_injected = false;
   uint32_t noise_epoch = 0;
 };
@@ -111,6 +113,10 @@ struct MppiHandle
   uint64_t fused_checked_key = ~0ull;
   bool fused_checked_ok = false;
   bool have_cycle = false;     // a cycle block is resident (mppi_enqueue_resident allowed)
+  bool resident_capture = false;  // keep pristine copies of the cycle inputs for mppi_enqueue_resident
+  bool use_graphs = true;      // MPPI_B200_NO_GRAPH=1 launches node by node
+  struct CycleGraph {uint64_t key; cudaGraphExec_t exec;};
+  std::vector<CycleGraph> graphs;  // one instantiated graph per launch-plan signature
   bool from_tensors_loaded = false;
   uint64_t launches = 0;
   bool timing = false;
@@ -128,6 +134,8 @@ struct MppiHandle
 
 namespace
 {
+
+void drop_graphs(MppiHandle * h);
 
 void free_device(MppiHandle * h)
 {
@@ -358,6 +366,7 @@ int validate_and_derive(MppiHandle * h, const MppiConfig & c, std::string & err)
 
 int allocate(MppiHandle * h)
 {
+  drop_graphs(h);
   free_device(h);
   const size_t R = h->R, B = h->B, T = h->T;
   const size_t bt = R * B * T;
@@ -450,6 +459,7 @@ int ensure_cycle_block(MppiHandle * h, int need_path)
     return MPPI_ERR_UNSUPPORTED;
   }
   CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
   if (h->h_cycle_block) {cudaFreeHost(h->h_cycle_block); h->h_cycle_block = nullptr;}
   if (h->d_cycle_block) {cudaFree(h->d_cycle_block); h->d_cycle_block = nullptr;}
   if (h->d_cycle_saved) {cudaFree(h->d_cycle_saved); h->d_cycle_saved = nullptr;}
@@ -832,6 +842,25 @@ int enqueue_iterations(MppiHandle * h, cudaStream_t stream, const LaunchPlan & p
   return MPPI_OK;
 }
 
+void drop_graphs(MppiHandle * h)
+{
+  for (auto & g : h->graphs) {cudaGraphExecDestroy(g.exec);}
+  h->graphs.clear();
+}
+
+// Everything that is baked into a captured cycle graph besides fixed device / pinned addresses.
+uint64_t plan_key(const MppiHandle * h, const LaunchPlan & p)
+{
+  uint64_t k = 1469598103934665603ull;
+  auto mix = [&](uint64_t v) {k = (k ^ v) * 1099511628211ull;};
+  mix(p.fused); mix(p.cluster_size); mix(p.sm_f.total); mix(p.sm_f.path_cap);
+  mix(p.sm_a.total); mix(p.sm_a.path_cap); mix(p.sm_a.noise_stages); mix(p.sm_a.off_win); mix(p.sm_a.off_ring);
+  mix(p.block_a); mix(p.block_b); mix(p.path_cap);
+  mix(p.ka.block); mix(p.ka.holo); mix(p.ka.full); mix(p.ka.crit_types); mix(p.ka.cc_step); mix(p.ka.pa_step);
+  mix(h->cycle_block_bytes); mix(h->max_path); mix(h->map_stride); mix(h->cfg.visualize);
+  return k;
+}
+
 int upload_cycle_block(MppiHandle * h, cudaStream_t stream)
 {
   CU_CHECK(h, cudaMemcpyAsync(h->d_cycle_block, h->h_cycle_block, h->cycle_block_bytes, cudaMemcpyHostToDevice, stream));
@@ -949,6 +978,8 @@ int mppi_create(const MppiConfig * cfg, MppiHandle ** out)
   {
     const char * e = std::getenv("MPPI_B200_NO_FUSED");
     h->allow_fused = !(e && e[0] == '1');
+    const char * g = std::getenv("MPPI_B200_NO_GRAPH");
+    h->use_graphs = !(g && g[0] == '1');
   }
   h->robots.assign(h->R, HostRobot());
   rc = allocate(h);
@@ -972,6 +1003,7 @@ int mppi_destroy(MppiHandle * h)
   if (!h) {return MPPI_OK;}
   cudaStreamSynchronize(h->stream);
   cudaStreamSynchronize(h->side);
+  drop_graphs(h);
   free_device(h);
   if (h->d_map) {cudaFree(h->d_map);}
   if (h->h_map_stage) {cudaFreeHost(h->h_map_stage);}
@@ -1060,6 +1092,7 @@ int mppi_upload_costmap(
     // (re)allocate the per-robot slabs; previously uploaded maps are re-sent from their host copies
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     CU_CHECK(h, cudaStreamSynchronize(h->side));
+    drop_graphs(h);
     if (h->d_map) {cudaFree(h->d_map); h->d_map = nullptr;}
     if (h->h_map_stage) {cudaFreeHost(h->h_map_stage); h->h_map_stage = nullptr;}
     h->map_stride = need;
@@ -1069,11 +1102,8 @@ int mppi_upload_costmap(
     CU_CHECK(h, cudaMallocHost(&h->h_map_stage, h->map_stage_bytes * h->R));
     for (int r = 0; r < h->R; ++r) {
       HostRobot & o = h->robots[r];
-      if (o.map_valid && static_cast<uint32_t>(r) != robot) {
-        CU_CHECK(h, cudaMemcpy2D(
-            h->d_map + h->map_stride * r, o.pitch, o.map_host.data(), o.size_x, o.size_x, o.size_y,
-            cudaMemcpyHostToDevice));
-      }
+      // maps uploaded before the slabs grew are gone with the old buffers: their robots must upload again
+      if (static_cast<uint32_t>(r) != robot) {o.map_valid = false; o.map_host = nullptr;}
     }
   }
   const size_t tight = static_cast<size_t>(size_x) * size_y;
@@ -1082,19 +1112,26 @@ int mppi_upload_costmap(
     if (h->h_map_stage) {cudaFreeHost(h->h_map_stage); h->h_map_stage = nullptr;}
     h->map_stage_bytes = tight;
     CU_CHECK(h, cudaMallocHost(&h->h_map_stage, h->map_stage_bytes * h->R));
+    for (int r = 0; r < h->R; ++r) {
+      if (static_cast<uint32_t>(r) != robot) {h->robots[r].map_valid = false; h->robots[r].map_host = nullptr;}
+    }
   }
   HostRobot & rb = h->robots[robot];
   // the previous async copy out of this staging slab must have drained before it is overwritten
   CU_CHECK(h, cudaStreamSynchronize(h->side));
   uint8_t * stage = h->h_map_stage + h->map_stage_bytes * robot;
   std::memcpy(stage, cells, tight);
-  rb.map_host.assign(cells, cells + tight);
+  rb.map_host = stage;
   rb.size_x = size_x; rb.size_y = size_y; rb.pitch = pitch;
   rb.resolution = resolution; rb.origin_x = origin_x; rb.origin_y = origin_y;
   rb.map_valid = true;
-  // pinned -> device on the side stream, tight rows -> 16-byte-pitched rows
-  CU_CHECK(h, cudaMemcpy2DAsync(
-      h->d_map + h->map_stride * robot, pitch, stage, size_x, size_x, size_y, cudaMemcpyHostToDevice, h->side));
+  // pinned -> device on the side stream, tight rows -> 16-byte-pitched rows (one flat copy when they coincide)
+  if (pitch == size_x) {
+    CU_CHECK(h, cudaMemcpyAsync(h->d_map + h->map_stride * robot, stage, tight, cudaMemcpyHostToDevice, h->side));
+  } else {
+    CU_CHECK(h, cudaMemcpy2DAsync(
+        h->d_map + h->map_stride * robot, pitch, stage, size_x, size_x, size_y, cudaMemcpyHostToDevice, h->side));
+  }
   CU_CHECK(h, cudaEventRecord(h->map_event, h->side));
   h->map_event_pending = true;
   return MPPI_OK;
@@ -1155,27 +1192,82 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
   const LaunchPlan plan = make_plan(h);
   bool first = true;
   while (true) {
-    rc = upload_cycle_block(h, h->stream);
-    if (rc != MPPI_OK) {return rc;}
-    if (first) {
-      // pristine copies for mppi_enqueue_resident
-      CU_CHECK(h, cudaMemcpyAsync(h->d_cycle_saved, h->d_cycle_block, h->cycle_block_bytes, cudaMemcpyDeviceToDevice, h->stream));
-      CU_CHECK(h, cudaMemcpyAsync(h->d_u_saved, h->d_u, sizeof(float) * 3 * h->T * h->R, cudaMemcpyDeviceToDevice, h->stream));
-      CU_CHECK(h, cudaMemcpyAsync(h->d_hist_saved, h->d_hist, sizeof(float) * 12 * h->R, cudaMemcpyDeviceToDevice, h->stream));
-      CU_CHECK(h, cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, h->stream));
-      first = false;
-    }
-    if (h->cfg.visualize) {
-      CU_CHECK(h, cudaMemsetAsync(h->d_collisions, 0, static_cast<size_t>(h->B) * h->R, h->stream));
-      if (h->d_critic_costs) {
-        CU_CHECK(h, cudaMemsetAsync(h->d_critic_costs, 0, sizeof(float) * h->cfg.n_critics * h->B * h->R, h->stream));
-      }
-    }
+    // One attempt = H2D of the cycle block, the optimize() iterations, D2H of the result block.  The
+    // common case (first attempt, own stream, no per-kernel timing) replays a captured CUDA graph:
+    // one launch call instead of one per node.  Addresses are fixed; the plan signature keys the cache.
+    const bool graphable = h->use_graphs && first && !h->resident_capture && !h->timing && h->stream == h->own_stream;
     rc = wait_map(h, h->stream);
     if (rc != MPPI_OK) {return rc;}
-    rc = enqueue_iterations(h, h->stream, plan);
-    if (rc != MPPI_OK) {return rc;}
-    CU_CHECK(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_stride * h->R, cudaMemcpyDeviceToHost, h->stream));
+    if (graphable) {
+      const uint64_t key = plan_key(h, plan);
+      cudaGraphExec_t exec = nullptr;
+      for (auto & g : h->graphs) {
+        if (g.key == key) {exec = g.exec; break;}
+      }
+      if (!exec) {
+        const uint64_t launches_before = h->launches;
+        CU_CHECK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int crc = upload_cycle_block(h, h->stream);
+        if (crc == MPPI_OK && cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, h->stream) != cudaSuccess) {crc = MPPI_ERR_CUDA;}
+        if (crc == MPPI_OK && h->cfg.visualize) {
+          if (cudaMemsetAsync(h->d_collisions, 0, static_cast<size_t>(h->B) * h->R, h->stream) != cudaSuccess) {crc = MPPI_ERR_CUDA;}
+          if (h->d_critic_costs &&
+            cudaMemsetAsync(h->d_critic_costs, 0, sizeof(float) * h->cfg.n_critics * h->B * h->R, h->stream) != cudaSuccess)
+          {
+            crc = MPPI_ERR_CUDA;
+          }
+        }
+        if (crc == MPPI_OK) {crc = enqueue_iterations(h, h->stream, plan);}
+        if (crc == MPPI_OK &&
+          cudaMemcpyAsync(h->h_out, h->d_out, h->out_stride * h->R, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
+        {
+          crc = MPPI_ERR_CUDA;
+        }
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        h->launches = launches_before;  // capture enqueued nothing; launches are counted per replay below
+        if (crc != MPPI_OK || ce != cudaSuccess || !graph) {
+          if (graph) {cudaGraphDestroy(graph);}
+          cudaGetLastError();
+          h->use_graphs = false;  // fall back to node-by-node launches for this handle
+          continue;
+        }
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+          cudaGetLastError();
+          h->use_graphs = false;
+          continue;
+        }
+        if (h->graphs.size() >= 16) {drop_graphs(h);}
+        h->graphs.push_back({key, exec});
+      }
+      CU_CHECK(h, cudaGraphLaunch(exec, h->stream));
+      h->launches += static_cast<uint64_t>(h->cfg.iteration_count) * (plan.fused ? 1 : 4);
+      first = false;
+    } else {
+      rc = upload_cycle_block(h, h->stream);
+      if (rc != MPPI_OK) {return rc;}
+      if (first) {
+        if (h->resident_capture) {
+          // pristine copies for mppi_enqueue_resident
+          CU_CHECK(h, cudaMemcpyAsync(h->d_cycle_saved, h->d_cycle_block, h->cycle_block_bytes, cudaMemcpyDeviceToDevice, h->stream));
+          CU_CHECK(h, cudaMemcpyAsync(h->d_u_saved, h->d_u, sizeof(float) * 3 * h->T * h->R, cudaMemcpyDeviceToDevice, h->stream));
+          CU_CHECK(h, cudaMemcpyAsync(h->d_hist_saved, h->d_hist, sizeof(float) * 12 * h->R, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        CU_CHECK(h, cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, h->stream));
+        first = false;
+      }
+      if (h->cfg.visualize) {
+        CU_CHECK(h, cudaMemsetAsync(h->d_collisions, 0, static_cast<size_t>(h->B) * h->R, h->stream));
+        if (h->d_critic_costs) {
+          CU_CHECK(h, cudaMemsetAsync(h->d_critic_costs, 0, sizeof(float) * h->cfg.n_critics * h->B * h->R, h->stream));
+        }
+      }
+      rc = enqueue_iterations(h, h->stream, plan);
+      if (rc != MPPI_OK) {return rc;}
+      CU_CHECK(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_stride * h->R, cudaMemcpyDeviceToHost, h->stream));
+    }
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     bool any_retry = false;
     for (int r = 0; r < h->R; ++r) {
@@ -1187,7 +1279,37 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
     }
     if (!any_retry) {break;}
   }
-  h->have_cycle = true;
+  h->have_cycle = h->resident_capture;
+  return MPPI_OK;
+}
+
+int mppi_set_resident_capture(MppiHandle * h, int enabled)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  h->resident_capture = enabled != 0;
+  if (!h->resident_capture) {h->have_cycle = false;}
+  return MPPI_OK;
+}
+
+// Times `cycles` back-to-back (mppi_upload_costmap; mppi_optimize) pairs for robot 0 .. n_robots-1 on the
+// calling thread with steady_clock: the end-to-end latency of the C ABI with host buffers, free of any
+// binding overhead.  per_call_seconds receives `cycles` entries.
+int mppi_time_e2e(
+  MppiHandle * h, const uint8_t * cells, uint32_t size_x, uint32_t size_y, double resolution, double origin_x,
+  double origin_y, const MppiCycleIn * in, MppiCycleOut * out, int cycles, double * per_call_seconds)
+{
+  if (!h || !cells || !in || !out || !per_call_seconds || cycles < 1) {return MPPI_ERR_INVALID_ARGUMENT;}
+  for (int i = 0; i < cycles; ++i) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < h->R; ++r) {
+      int rc = mppi_upload_costmap(h, static_cast<uint32_t>(r), cells, size_x, size_y, resolution, origin_x, origin_y);
+      if (rc != MPPI_OK) {return rc;}
+    }
+    int rc = mppi_optimize(h, in, out);
+    if (rc != MPPI_OK) {return rc;}
+    const auto t1 = std::chrono::steady_clock::now();
+    per_call_seconds[i] = std::chrono::duration<double>(t1 - t0).count();
+  }
   return MPPI_OK;
 }
 

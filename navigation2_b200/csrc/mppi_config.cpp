@@ -172,7 +172,7 @@ const char * mppi_status_string(int status)
     case MPPI_ERR_CUDA: return "CUDA error (no CPU fallback exists)";
     case MPPI_ERR_NO_VALID_CONTROL: return "no valid control (nav2_core::NoValidControl)";
     case MPPI_ERR_CONFIG: return "configuration error (nav2_core::ControllerException)";
-    case MPPI_ERR_NOT_READY: return "no costmap uploaded";
+    case MPPI_ERR_NOT_READY: return "not ready";
     case MPPI_ERR_UNSUPPORTED: return "unsupported";
     default: return "unknown status";
   }

@@ -282,6 +282,22 @@ class Optimizer(EngineBase):
         _raise_for(self._lib, self._h, self._lib.mppi_set_state(self._h, robot, C.byref(st)))
 
     # -- measurement -------------------------------------------------------------------------
+    def setResidentCapture(self, enabled: bool) -> None:
+        _raise_for(self._lib, self._h, self._lib.mppi_set_resident_capture(self._h, 1 if enabled else 0))
+
+    def timeE2E(self, cells: np.ndarray, resolution: float, origin, inputs, cycles: int) -> np.ndarray:
+        """Per-call seconds of `cycles` (upload costmap; optimize) pairs, timed inside the C library."""
+        ins = [inputs] if isinstance(inputs, CycleInput) else list(inputs)
+        c_in = (capi.MppiCycleIn * self.R)(*[i.to_c() for i in ins])
+        c_out = (capi.MppiCycleOut * self.R)()
+        cells = np.ascontiguousarray(cells, dtype=np.uint8)
+        t = np.zeros(cycles, dtype=np.float64)
+        rc = self._lib.mppi_time_e2e(
+            self._h, cells.ctypes.data_as(C.POINTER(C.c_uint8)), cells.shape[1], cells.shape[0], float(resolution),
+            float(origin[0]), float(origin[1]), c_in, c_out, int(cycles), t.ctypes.data_as(C.POINTER(C.c_double)))
+        _raise_for(self._lib, self._h, rc)
+        return t
+
     def enqueueResident(self, cuda_stream: int | None = None) -> None:
         _raise_for(self._lib, self._h, self._lib.mppi_enqueue_resident(self._h, cuda_stream))
 

@@ -88,3 +88,39 @@ class ShardedOptimizer(Optimizer):
         if raise_on_failure and res.status != capi.MPPI_OK:
             _raise_for(lib, h, res.status)
         return res
+
+
+# ---- host restatement of the two exchanges (what kernels A / D2 do on the device), used by the
+# ---- world_size-2 gloo tests on CPU and as executable documentation of the protocol ----
+
+def encode_min(values: np.ndarray) -> np.ndarray:
+    """float32 -> int32 such that MAX over the codes is MIN over the floats (kernel: enc_min)."""
+    i = np.asarray(values, dtype=np.float32).view(np.int32).astype(np.int64)
+    ordered = np.where(i >= 0, i, i ^ 0x7FFFFFFF)
+    return (~ordered).astype(np.int32)
+
+
+def decode_min(codes: np.ndarray) -> np.ndarray:
+    o = (~np.asarray(codes, dtype=np.int32).astype(np.int64))
+    bits = np.where(o >= 0, o, o ^ 0x7FFFFFFF).astype(np.int32)
+    return bits.view(np.float32)
+
+
+def local_slot(costs: np.ndarray, cv: np.ndarray, inv_temp: float) -> np.ndarray:
+    """One rank's AR-2 slot: (min cost, sum of exp(-(c - min)/T), weighted control sums [3T]).
+    costs: (B_local,), cv: (3, T, B_local)."""
+    m = np.float32(costs.min())
+    w = np.exp(-np.float32(inv_temp) * (costs.astype(np.float32) - m)).astype(np.float32)
+    W = (cv.astype(np.float64) * w.astype(np.float64)[None, None, :]).sum(axis=2)
+    return np.concatenate([[m, w.astype(np.float64).sum()], W.reshape(-1)]).astype(np.float32)
+
+
+def combine_slots(slots: np.ndarray, inv_temp: float) -> np.ndarray:
+    """All-gathered slots (world, 2 + 3T) -> softmax-weighted mean control sequence (3T,),
+    rescaling every rank by exp(-(m_g - m)/temperature) (kernel D2)."""
+    slots = np.asarray(slots, dtype=np.float32)
+    m = slots[:, 0].min()
+    scale = np.exp(-np.float32(inv_temp) * (slots[:, 0] - m)).astype(np.float64)
+    S = (slots[:, 1].astype(np.float64) * scale).sum()
+    W = (slots[:, 2:].astype(np.float64) * scale[:, None]).sum(axis=0)
+    return (W / S).astype(np.float32)
