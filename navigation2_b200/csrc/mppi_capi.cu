@@ -44,6 +44,8 @@ struct HostRobot
                                        // validity is evaluated on the host from it, O(n_path) lookups
   bool noise_injected = false;
   uint32_t noise_epoch = 0;
+  cudaEvent_t stage_event = nullptr;   // completion of the last H2D copy out of this robot's staging slab
+  bool stage_pending = false;
 };
 
 #define CU_CHECK(h, call) \
@@ -793,6 +795,10 @@ LaunchPlan make_plan(MppiHandle * h)
   if (h->allow_fused && h->cfg.shard_world == 1 && !p.ka.full && h->B <= MPPI_FUSED_G * MPPI_FUSED_MAX_CLUSTER) {
     int cs = 1;
     while (cs * MPPI_FUSED_G < h->B) {cs *= 2;}
+    // The fused kernel trades throughput for latency (one 512-thread CTA per SM, serial phases): it is
+    // the right tool while all clusters fit one wave of the 148 SMs.  Larger fleets are throughput-bound
+    // and go through the general thread-per-trajectory kernels with a (blocks, robots) grid.
+    const bool one_wave = static_cast<long long>(cs) * h->R <= 148;
     p.cluster_size = cs;
     p.sm_f = mppi_smem_layout_f(h->T, h->holo, p.path_cap, static_cast<int>(h->cfg.n_critics) + 3, obstacles, win_bytes);
     if (p.sm_f.total <= 227u * 1024u) {
@@ -801,7 +807,7 @@ LaunchPlan make_plan(MppiHandle * h)
         h->fused_checked_key = key;
         h->fused_checked_ok = mppi_fused_supported(p.sm_f, h->holo, cs);
       }
-      p.fused = h->fused_checked_ok;
+      p.fused = h->fused_checked_ok && one_wave;
     }
   }
   return p;
@@ -1008,6 +1014,7 @@ int mppi_destroy(MppiHandle * h)
   if (h->d_map) {cudaFree(h->d_map);}
   if (h->h_map_stage) {cudaFreeHost(h->h_map_stage);}
   for (auto & p : h->timing_events) {cudaEventDestroy(p.first); cudaEventDestroy(p.second);}
+  for (auto & rb : h->robots) {if (rb.stage_event) {cudaEventDestroy(rb.stage_event);}}
   cudaEventDestroy(h->map_event);
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->side);
@@ -1117,8 +1124,12 @@ int mppi_upload_costmap(
     }
   }
   HostRobot & rb = h->robots[robot];
-  // the previous async copy out of this staging slab must have drained before it is overwritten
-  CU_CHECK(h, cudaStreamSynchronize(h->side));
+  // the previous async copy out of THIS robot's staging slab must have drained before it is overwritten
+  if (rb.stage_pending) {
+    CU_CHECK(h, cudaEventSynchronize(rb.stage_event));
+    rb.stage_pending = false;
+  }
+  if (!rb.stage_event) {CU_CHECK(h, cudaEventCreateWithFlags(&rb.stage_event, cudaEventDisableTiming));}
   uint8_t * stage = h->h_map_stage + h->map_stage_bytes * robot;
   std::memcpy(stage, cells, tight);
   rb.map_host = stage;
@@ -1132,6 +1143,8 @@ int mppi_upload_costmap(
     CU_CHECK(h, cudaMemcpy2DAsync(
         h->d_map + h->map_stride * robot, pitch, stage, size_x, size_x, size_y, cudaMemcpyHostToDevice, h->side));
   }
+  CU_CHECK(h, cudaEventRecord(rb.stage_event, h->side));
+  rb.stage_pending = true;
   CU_CHECK(h, cudaEventRecord(h->map_event, h->side));
   h->map_event_pending = true;
   return MPPI_OK;
