@@ -356,6 +356,10 @@ int mppi_set_state(MppiHandle * h, uint32_t robot, const MppiOptimizerState * st
  * no H2D, no D2H, no host sync.  The control sequence is restored first so every call does
  * identical work. */
 int mppi_enqueue_resident(MppiHandle * h, void * cuda_stream);
+/* The scoring pass alone (kernel A in score_tensors mode + kernel B) on the state / trajectory tensors the
+ * last mppi_optimize materialised (materialize_tensors = 1), everything resident: the kernel the
+ * reference's critics correspond to, for roofline measurement. */
+int mppi_enqueue_score_resident(MppiHandle * h, void * cuda_stream);
 /* mppi_enqueue_resident replays the inputs of the last mppi_optimize; keeping the pristine copies it
  * needs costs three small device copies per cycle, so it is opt-in. */
 int mppi_set_resident_capture(MppiHandle * h, int enabled);

@@ -58,15 +58,11 @@ MPPI_HD void mppi_sincosf(float x, float * s_out, float * c_out)
   float pc = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
   pc = fmaf(pc, z, 4.166664568298827e-2f);
   const float cs = fmaf(pc * z, z, fmaf(-0.5f, z, 1.0f));
-  float s, c;
-  switch (q) {
-    case 0: s = sn; c = cs; break;
-    case 1: s = cs; c = -sn; break;
-    case 2: s = -sn; c = -cs; break;
-    default: s = -cs; c = sn; break;
-  }
-  *s_out = s;
-  *c_out = c;
+  /* quadrant: q odd swaps sin/cos; sin is negated for q = 2, 3 and cos for q = 1, 2 */
+  const float a = (q & 1) ? cs : sn;
+  const float b = (q & 1) ? sn : cs;
+  *s_out = (q & 2) ? -a : a;
+  *c_out = ((q + 1) & 2) ? -b : b;
 }
 
 /* utils.hpp:254-262 normalize_angles (float, Eigen side): fmodf is exact on CPU and GPU. */

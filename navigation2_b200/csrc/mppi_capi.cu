@@ -111,6 +111,9 @@ struct MppiHandle
   uint8_t * h_map_stage = nullptr;
   size_t map_stage_bytes = 0;
 
+  bool host_timers = false;    // MPPI_B200_HOST_TIMERS=1: accumulate host-side phase times, printed by mppi_destroy
+  double ht[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t ht_n = 0;
   bool allow_fused = true;     // MPPI_B200_NO_FUSED=1 forces the general four-kernel path
   uint64_t fused_checked_key = ~0ull;
   bool fused_checked_ok = false;
@@ -148,7 +151,8 @@ void free_device(MppiHandle * h)
   F(h->d_u); F(h->d_u_saved); F(h->d_hist); F(h->d_hist_saved); F(h->d_terms); F(h->d_obs_raw);
   F(h->d_obs_rep); F(h->d_last); F(h->d_pa); F(h->d_costs); F(h->d_softmax); F(h->d_critic_costs);
   F(h->d_collisions); F(h->d_dbg_cost); F(h->d_dbg_obs); F(h->d_red); F(h->d_partials); F(h->d_slot);
-  F(h->d_phase_clocks); F(h->d_slot_all); F(h->d_static); F(h->d_cycle_block); F(h->d_cycle_saved); F(h->d_out);
+  F(h->d_phase_clocks); F(h->d_slot_all); F(h->d_static); F(h->d_cycle_block); F(h->d_cycle_saved);
+  h->d_out = nullptr;  // alias of the mapped h_out
   if (h->h_cycle_block) {cudaFreeHost(h->h_cycle_block); h->h_cycle_block = nullptr;}
   if (h->h_out) {cudaFreeHost(h->h_out); h->h_out = nullptr;}
 }
@@ -432,7 +436,10 @@ int allocate(MppiHandle * h)
     }
     CU_CHECK(h, cudaMemcpy(h->d_red, init.data(), init.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
-  h->n_partial_blocks = static_cast<int>(std::min<size_t>((B + MPPI_BLOCK_C - 1) / MPPI_BLOCK_C, MPPI_MAX_PARTIAL_BLOCKS));
+  {
+    const size_t tile = static_cast<size_t>(MPPI_BLOCK_C) * ((B % 4 == 0) ? 4 : 1);  // trajectories per block pass
+    h->n_partial_blocks = static_cast<int>(std::min<size_t>((B + tile - 1) / tile, MPPI_MAX_PARTIAL_BLOCKS * 2));
+  }
   if (R > 1) {
     // fleet: keep the total grid near two waves of 148 SMs
     const int per_robot = std::max<int>(1, static_cast<int>(MPPI_MAX_PARTIAL_BLOCKS / R));
@@ -445,9 +452,11 @@ int allocate(MppiHandle * h)
   CU_CHECK(h, cudaMemcpy(h->d_static, &h->h_static, sizeof(DevStatic), cudaMemcpyHostToDevice));
   h->max_path = 256;
   h->out_stride = (sizeof(DevOutHeader) + 6 * T * sizeof(float) + 15) & ~static_cast<size_t>(15);
-  CU_CHECK(h, cudaMalloc(&h->d_out, R * h->out_stride));
-  CU_CHECK(h, cudaMemset(h->d_out, 0, R * h->out_stride));
-  CU_CHECK(h, cudaMallocHost(&h->h_out, R * h->out_stride));
+  // result blocks live in mapped pinned host memory: the finalize kernel's ~1.4 KB per robot goes straight over
+  // PCIe as posted writes and is visible to the host after the stream synchronises (no D2H copy node)
+  CU_CHECK(h, cudaHostAlloc(&h->h_out, R * h->out_stride, cudaHostAllocMapped));
+  std::memset(h->h_out, 0, R * h->out_stride);
+  CU_CHECK(h, cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->d_out), h->h_out, 0));
   return MPPI_OK;
 }
 
@@ -813,12 +822,13 @@ LaunchPlan make_plan(MppiHandle * h)
   return p;
 }
 
-int enqueue_iterations(MppiHandle * h, cudaStream_t stream, const LaunchPlan & plan)
+int enqueue_iterations(MppiHandle * h, cudaStream_t stream, const LaunchPlan & plan, bool fresh_costs = false)
 {
   KArgs a = make_args(h);
   const int iters = static_cast<int>(h->cfg.iteration_count);
   for (int it = 0; it < iters; ++it) {
     a.last_iteration = (it == iters - 1) ? 1 : 0;
+    a.zero_costs = (fresh_costs && it == 0) ? 1 : 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
       if (h->timing_used == h->timing_events.size()) {
@@ -986,6 +996,8 @@ int mppi_create(const MppiConfig * cfg, MppiHandle ** out)
     h->allow_fused = !(e && e[0] == '1');
     const char * g = std::getenv("MPPI_B200_NO_GRAPH");
     h->use_graphs = !(g && g[0] == '1');
+    const char * t = std::getenv("MPPI_B200_HOST_TIMERS");
+    h->host_timers = t && t[0] == '1';
   }
   h->robots.assign(h->R, HostRobot());
   rc = allocate(h);
@@ -1009,6 +1021,12 @@ int mppi_destroy(MppiHandle * h)
   if (!h) {return MPPI_OK;}
   cudaStreamSynchronize(h->stream);
   cudaStreamSynchronize(h->side);
+  if (h->host_timers && h->ht_n) {
+    const double n = static_cast<double>(h->ht_n);
+    std::fprintf(stderr, "[mppi host timers, us/cycle over %llu cycles] upload_costmap %.1f  prepare %.1f  plan %.1f  "
+      "enqueue %.1f  sync %.1f  finish %.1f\n", static_cast<unsigned long long>(h->ht_n), 1e6 * h->ht[0] / n,
+      1e6 * h->ht[1] / n, 1e6 * h->ht[2] / n, 1e6 * h->ht[3] / n, 1e6 * h->ht[4] / n, 1e6 * h->ht[5] / n);
+  }
   drop_graphs(h);
   free_device(h);
   if (h->d_map) {cudaFree(h->d_map);}
@@ -1093,6 +1111,7 @@ int mppi_upload_costmap(
     if (h) {h->error = "bad costmap arguments";}
     return MPPI_ERR_INVALID_ARGUMENT;
   }
+  const auto ht0 = std::chrono::steady_clock::now();
   const uint32_t pitch = (size_x + 15u) & ~15u;
   const size_t need = static_cast<size_t>(pitch) * size_y;
   if (need > h->map_stride) {
@@ -1147,6 +1166,7 @@ int mppi_upload_costmap(
   rb.stage_pending = true;
   CU_CHECK(h, cudaEventRecord(h->map_event, h->side));
   h->map_event_pending = true;
+  if (h->host_timers) {h->ht[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - ht0).count();}
   return MPPI_OK;
 }
 
@@ -1196,13 +1216,24 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
       }
     }
   }
+  using clk = std::chrono::steady_clock;
+  auto tick = [&](int slot, clk::time_point & t0) {
+      if (h->host_timers) {
+        const auto t1 = clk::now();
+        h->ht[slot] += std::chrono::duration<double>(t1 - t0).count();
+        t0 = t1;
+      }
+    };
+  clk::time_point tp = clk::now();
   for (int r = 0; r < h->R; ++r) {
     out[r].retries = 0;
     out[r].status = MPPI_OK;
     rc = prepare_robot(h, r, in[r], -1, false);
     if (rc != MPPI_OK) {return rc;}
   }
+  tick(1, tp);
   const LaunchPlan plan = make_plan(h);
+  tick(2, tp);
   bool first = true;
   while (true) {
     // One attempt = H2D of the cycle block, the optimize() iterations, D2H of the result block.  The
@@ -1221,7 +1252,6 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
         const uint64_t launches_before = h->launches;
         CU_CHECK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         int crc = upload_cycle_block(h, h->stream);
-        if (crc == MPPI_OK && cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, h->stream) != cudaSuccess) {crc = MPPI_ERR_CUDA;}
         if (crc == MPPI_OK && h->cfg.visualize) {
           if (cudaMemsetAsync(h->d_collisions, 0, static_cast<size_t>(h->B) * h->R, h->stream) != cudaSuccess) {crc = MPPI_ERR_CUDA;}
           if (h->d_critic_costs &&
@@ -1230,12 +1260,8 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
             crc = MPPI_ERR_CUDA;
           }
         }
-        if (crc == MPPI_OK) {crc = enqueue_iterations(h, h->stream, plan);}
-        if (crc == MPPI_OK &&
-          cudaMemcpyAsync(h->h_out, h->d_out, h->out_stride * h->R, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess)
-        {
-          crc = MPPI_ERR_CUDA;
-        }
+        // the finalize kernel writes the result block straight into mapped pinned host memory: no D2H node
+        if (crc == MPPI_OK) {crc = enqueue_iterations(h, h->stream, plan, true);}
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
         h->launches = launches_before;  // capture enqueued nothing; launches are counted per replay below
@@ -1279,9 +1305,10 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
       }
       rc = enqueue_iterations(h, h->stream, plan);
       if (rc != MPPI_OK) {return rc;}
-      CU_CHECK(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_stride * h->R, cudaMemcpyDeviceToHost, h->stream));
     }
+    tick(3, tp);
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    tick(4, tp);
     bool any_retry = false;
     for (int r = 0; r < h->R; ++r) {
       if (!h->hcyc(r)->run) {continue;}  // finished in an earlier attempt
@@ -1290,8 +1317,10 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
       if (rc != MPPI_OK) {return rc;}
       any_retry = any_retry || retry;
     }
+    tick(5, tp);
     if (!any_retry) {break;}
   }
+  h->ht_n++;
   h->have_cycle = h->resident_capture;
   return MPPI_OK;
 }
@@ -1381,7 +1410,6 @@ int mppi_score_tensors(
   if (collisions) {
     CU_CHECK(h, cudaMemcpyAsync(collisions, h->d_collisions + static_cast<size_t>(robot) * h->B, h->B, cudaMemcpyDeviceToHost, h->stream));
   }
-  CU_CHECK(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_stride * h->R, cudaMemcpyDeviceToHost, h->stream));
   // reset the reduction words this call dirtied (the finalize kernel does it on the normal path)
   {
     int32_t init[RED_WORDS] = {0, INT32_MIN, 0, 0, INT32_MIN, 0, 0, 0};
@@ -1514,6 +1542,46 @@ int mppi_enqueue_resident(MppiHandle * h, void * cuda_stream)
   return enqueue_iterations(h, s, plan);
 }
 
+int mppi_enqueue_score_resident(MppiHandle * h, void * cuda_stream)
+{
+  if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
+  if (!h->have_cycle || !h->d_state[0]) {
+    h->error = "mppi_enqueue_score_resident needs materialize_tensors, resident capture and a preceding mppi_optimize";
+    return MPPI_ERR_NOT_READY;
+  }
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  CU_CHECK(h, cudaMemcpyAsync(h->d_cycle_block, h->d_cycle_saved, h->cycle_block_bytes, cudaMemcpyDeviceToDevice, s));
+  CU_CHECK(h, cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, s));
+  const LaunchPlan plan = make_plan(h);
+  KArgs a = make_args(h);
+  a.materialize = 0;
+  KPlanA ka = plan.ka;
+  ka.from_tensors = true;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing) {
+    if (h->timing_used == h->timing_events.size()) {
+      cudaEvent_t x, y;
+      CU_CHECK(h, cudaEventCreate(&x));
+      CU_CHECK(h, cudaEventCreate(&y));
+      h->timing_events.emplace_back(x, y);
+    }
+    e0 = h->timing_events[h->timing_used].first;
+    e1 = h->timing_events[h->timing_used].second;
+    h->timing_used++;
+    CU_CHECK(h, cudaEventRecord(e0, s));
+  }
+  CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_tensors, ka, s));
+  if (h->timing) {CU_CHECK(h, cudaEventRecord(e1, s));}
+  CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, true, plan.block_b, s));
+  // the reduction words this pass dirtied are reset by the next mppi_optimize's finalize kernel; do it here too
+  static const int32_t init[RED_WORDS] = {0, INT32_MIN, 0, 0, INT32_MIN, 0, 0, 0};
+  for (int r = 0; r < h->R; ++r) {
+    CU_CHECK(h, cudaMemcpyAsync(h->d_red + r * RED_WORDS, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  }
+  h->launches += 2;
+  return MPPI_OK;
+}
+
 uint64_t mppi_launch_count(const MppiHandle * h) {return h ? h->launches : 0;}
 
 int mppi_set_kernel_timing(MppiHandle * h, int enabled)
@@ -1624,7 +1692,6 @@ int mppi_shard_update(MppiHandle * h, int last_iteration)
 int mppi_shard_end(MppiHandle * h, MppiCycleOut * out)
 {
   if (!h || !out) {return MPPI_ERR_INVALID_ARGUMENT;}
-  CU_CHECK(h, cudaMemcpyAsync(h->h_out, h->d_out, h->out_stride * h->R, cudaMemcpyDeviceToHost, h->stream));
   CU_CHECK(h, cudaStreamSynchronize(h->stream));
   int result = MPPI_OK;
   for (int r = 0; r < h->R; ++r) {

@@ -149,6 +149,7 @@ struct KArgs
   int32_t materialize;
   int32_t last_iteration;
   int32_t do_shift;
+  int32_t zero_costs;   // first iteration of an evalControl call: costs_ start from zero (optimizer.cpp:335) without a memset
   // noise [R][T][B]
   const float * noise_vx;
   const float * noise_vy;

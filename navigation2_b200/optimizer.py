@@ -301,6 +301,9 @@ class Optimizer(EngineBase):
     def enqueueResident(self, cuda_stream: int | None = None) -> None:
         _raise_for(self._lib, self._h, self._lib.mppi_enqueue_resident(self._h, cuda_stream))
 
+    def enqueueScoreResident(self, cuda_stream: int | None = None) -> None:
+        _raise_for(self._lib, self._h, self._lib.mppi_enqueue_score_resident(self._h, cuda_stream))
+
     def synchronize(self) -> None:
         _raise_for(self._lib, self._h, self._lib.mppi_device_synchronize(self._h))
 

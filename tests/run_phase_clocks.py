@@ -17,6 +17,7 @@ names = ["start", "issued loads", "loads landed", "P1 vel chains", "P2 sincos", 
          "block_b", "P5 path+cost", "xch2 sync", "P6 softmax+wsum", "xch3 sync", "combine+sync", "finalize"]
 c = clk[0]
 print("fine marks rank 0 (relative to start):", {k: int(c[k] - c[0]) for k in range(16, 22) if c[k]}, "mark1", int(c[1]-c[0]), "mark5", int(c[5]-c[0]), "mark6", int(c[6]-c[0]))
+print("finalize marks (delta cycles):", [int(c[k] - c[k-1]) for k in range(23, 32) if c[k] and c[k-1]], "first", int(c[22] - c[13]) if c[22] else None)
 for rank in (0,):
     c = clk[rank]
     print("rank", rank, "total cycles", c[13] - c[0], "(+finalize", c[14] - c[13] if c[14] else 0, ")")
