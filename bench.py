@@ -137,6 +137,16 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        e = json.load(open(p))[key]
+        return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def setup_engine(wl, cfg=None, seed=42):
     import navigation2_b200 as nb
     from navigation2_b200 import scenarios as S
@@ -368,11 +378,14 @@ def run_ours(args):
         pass
     alg_bytes = algorithmic_bytes_kernel_a(cfg, win)
     achieved = alg_bytes / (ka_ms * 1e-3) / 1e9 if ka_ms > 0 else 0.0
-    roofline = {"kernel": "k_rollout_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+    fused = launches_timed <= args.steps * iters + 1
+    roofline = {"kernel": "k_fused_cluster (rollout + all critics + softmax update, one launch)" if fused else "k_rollout_score",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": measured_traffic("k_fused_cluster@C1") if fused and args.workload == "c1" else None,
+                "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": ka_ms, "launches_timed": ka_n, "peak_source": peak_src,
-                "note": "C1 moves <1 MB per launch and is launch/latency-bound (SURVEY.md §8d); see roofline_large_batch "
-                        "for the same kernel on a batch larger than L2"}
+                "note": "C1 moves <1 MB per launch: it is latency-bound (0.9 MB at HBM speed is 0.14 us), not bandwidth-bound "
+                        "(SURVEY.md §8d); roofline_large_batch has the HBM-regime kernels on a batch larger than L2"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -417,13 +430,23 @@ def large_batch_roofline(peak, peak_src, stream, flush):
     opt.setKernelTiming(True)
     step_ms = time_resident(opt, 10, 3, flush, stream)
     ka_ms, ka_n = opt.kernelTimeMs(reset=True)
+    kc_ms, kc_n = opt.kernelCTimeMs(reset=True)
     win = 0
     alg = algorithmic_bytes_kernel_a(cfg, win)
     achieved = alg / (ka_ms * 1e-3) / 1e9
     units = int(cfg.batch_size) * int(cfg.time_steps)
-    out = {"kernel": "k_rollout_score", "workload": "DiffDrive 1048576x56 (configs[3] on one GPU), default critics, Philox noise",
-           "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # kernel C re-reads the noise columns once (4 B x axes per trajectory-step) + cost and weight per trajectory
+    alg_c = units * 8 + int(cfg.batch_size) * 12
+    achieved_c = alg_c / (kc_ms * 1e-3) / 1e9 if kc_ms > 0 else 0.0
+    out = {"workload": "DiffDrive 1048576x56 (configs[3] on one GPU), default critics, Philox noise",
+           "kernel": "k_rollout_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+           "frac": achieved / peak, "traffic": measured_traffic("k_rollout_score@2^20x56"),
            "algorithmic_bytes_per_launch": alg, "kernel_ms": ka_ms, "launches_timed": ka_n, "peak_source": peak_src,
+           "limiter": "instruction issue (ncu: issue slots ~70% busy at 185 instructions per trajectory-step: IEEE sqrt, "
+                      "two IEEE divisions per costmap lookup, sin/cos per step), not HBM",
+           "kernel_c": {"kernel": "k_softmax_partial", "bound": "hbm", "achieved": achieved_c, "peak": peak, "unit": "GB/s",
+                        "frac": achieved_c / peak, "traffic": measured_traffic("k_softmax_partial@2^20x56"),
+                        "algorithmic_bytes_per_launch": alg_c, "kernel_ms": kc_ms, "launches_timed": kc_n},
            "step_ms": float(np.mean(step_ms)), "value": units / (float(np.mean(step_ms)) * 1e-3), "unit_value": UNIT}
     opt.shutdown()
     return out

@@ -375,6 +375,8 @@ uint64_t mppi_launch_count(const MppiHandle * h);
  * reset != 0; enabled by mppi_set_kernel_timing(h, 1).  Milliseconds per launch. */
 int mppi_set_kernel_timing(MppiHandle * h, int enabled);
 int mppi_kernel_time_ms(MppiHandle * h, int reset, double * ms_per_launch, uint64_t * launches);
+/* Same for kernel C (softmax weights + weighted control sums), the HBM-bound kernel of large batches. */
+int mppi_kernel_c_time_ms(MppiHandle * h, int reset, double * ms_per_launch, uint64_t * launches);
 /* The stream the handle launches on (cudaStream_t), for event timing by the caller. */
 void * mppi_stream(MppiHandle * h);
 /* Launch on the caller's stream instead (e.g. the stream torch.distributed orders its NCCL

@@ -213,6 +213,7 @@ SYMBOLS = {
     "mppi_launch_count": (C.c_uint64, [_P]),
     "mppi_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "mppi_kernel_time_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "mppi_kernel_c_time_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "mppi_stream": (_P, [_P]),
     "mppi_set_stream": (C.c_int, [_P, _P]),
     "mppi_device_synchronize": (C.c_int, [_P]),

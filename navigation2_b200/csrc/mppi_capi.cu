@@ -125,8 +125,10 @@ struct MppiHandle
   bool from_tensors_loaded = false;
   uint64_t launches = 0;
   bool timing = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;    // around kernel A (or the fused kernel)
   size_t timing_used = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events_c;  // around kernel C (softmax partials)
+  size_t timing_used_c = 0;
 
   DevCycle * hcyc(int r) {return reinterpret_cast<DevCycle *>(h_cycle_block) + r;}
   float * hpath(int r) {
@@ -851,7 +853,21 @@ int enqueue_iterations(MppiHandle * h, cudaStream_t stream, const LaunchPlan & p
     CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, plan.ka, stream));
     if (h->timing) {CU_CHECK(h, cudaEventRecord(e1, stream));}
     CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, false, plan.block_b, stream));
+    cudaEvent_t c0 = nullptr, c1 = nullptr;
+    if (h->timing) {
+      if (h->timing_used_c == h->timing_events_c.size()) {
+        cudaEvent_t x, y;
+        CU_CHECK(h, cudaEventCreate(&x));
+        CU_CHECK(h, cudaEventCreate(&y));
+        h->timing_events_c.emplace_back(x, y);
+      }
+      c0 = h->timing_events_c[h->timing_used_c].first;
+      c1 = h->timing_events_c[h->timing_used_c].second;
+      h->timing_used_c++;
+      CU_CHECK(h, cudaEventRecord(c0, stream));
+    }
     CU_CHECK(h, mppi_launch_softmax_partial(a, h->holo, stream));
+    if (h->timing) {CU_CHECK(h, cudaEventRecord(c1, stream));}
     CU_CHECK(h, mppi_launch_finalize(a, h->holo, 0, stream));
     h->launches += 4;
   }
@@ -1032,6 +1048,7 @@ int mppi_destroy(MppiHandle * h)
   if (h->d_map) {cudaFree(h->d_map);}
   if (h->h_map_stage) {cudaFreeHost(h->h_map_stage);}
   for (auto & p : h->timing_events) {cudaEventDestroy(p.first); cudaEventDestroy(p.second);}
+  for (auto & p : h->timing_events_c) {cudaEventDestroy(p.first); cudaEventDestroy(p.second);}
   for (auto & rb : h->robots) {if (rb.stage_event) {cudaEventDestroy(rb.stage_event);}}
   cudaEventDestroy(h->map_event);
   cudaStreamDestroy(h->own_stream);
@@ -1589,6 +1606,7 @@ int mppi_set_kernel_timing(MppiHandle * h, int enabled)
   if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
   h->timing = enabled != 0;
   h->timing_used = 0;
+  h->timing_used_c = 0;
   return MPPI_OK;
 }
 
@@ -1605,6 +1623,22 @@ int mppi_kernel_time_ms(MppiHandle * h, int reset, double * ms_per_launch, uint6
   *ms_per_launch = h->timing_used ? total / static_cast<double>(h->timing_used) : 0.0;
   if (launches) {*launches = h->timing_used;}
   if (reset) {h->timing_used = 0;}
+  return MPPI_OK;
+}
+
+int mppi_kernel_c_time_ms(MppiHandle * h, int reset, double * ms_per_launch, uint64_t * launches)
+{
+  if (!h || !ms_per_launch) {return MPPI_ERR_INVALID_ARGUMENT;}
+  CU_CHECK(h, cudaDeviceSynchronize());
+  double total = 0.0;
+  for (size_t i = 0; i < h->timing_used_c; ++i) {
+    float ms = 0.0f;
+    CU_CHECK(h, cudaEventElapsedTime(&ms, h->timing_events_c[i].first, h->timing_events_c[i].second));
+    total += ms;
+  }
+  *ms_per_launch = h->timing_used_c ? total / static_cast<double>(h->timing_used_c) : 0.0;
+  if (launches) {*launches = h->timing_used_c;}
+  if (reset) {h->timing_used_c = 0;}
   return MPPI_OK;
 }
 

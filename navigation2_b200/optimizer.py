@@ -316,6 +316,12 @@ class Optimizer(EngineBase):
     def setKernelTiming(self, enabled: bool) -> None:
         _raise_for(self._lib, self._h, self._lib.mppi_set_kernel_timing(self._h, 1 if enabled else 0))
 
+    def kernelCTimeMs(self, reset: bool = True) -> tuple[float, int]:
+        ms = C.c_double(0.0)
+        n = C.c_uint64(0)
+        _raise_for(self._lib, self._h, self._lib.mppi_kernel_c_time_ms(self._h, 1 if reset else 0, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
+
     def kernelTimeMs(self, reset: bool = True) -> tuple[float, int]:
         ms = C.c_double(0.0)
         n = C.c_uint64(0)
