@@ -198,3 +198,155 @@ def test_near_goal_and_empty_path_lean():
     _lean_pair_check(cfg, cells, short, (10.0, 10.0, 0.2), (0.1, 0.0, 0.0), 3, "near-goal")
     empty = np.zeros((0, 3))
     _lean_pair_check(cfg, cells, empty, (10.0, 10.0, 0.2), (0.1, 0.0, 0.0), 2, "empty-path")
+
+
+@pytest.mark.parametrize("model", ["diff_drive", "omni"])
+def test_input_delay_and_clamp_raw_controls(model):
+    """MotionModel::predict's input-delay shift (motion_models.hpp:160-216, per-axis offsets from
+    model_delay_*) and clamp_raw_controls write-back (:131-156), which also changes what the softmax
+    update averages (optimizer.cpp:610-640)."""
+    cfg = P.make_config(
+        {"batch_size": 1500, "time_steps": 56, "motion_model": model, "controller_frequency": 20.0,
+         "model_delay_vx": 0.10, "model_delay_vy": 0.15, "model_delay_wz": 0.20, "clamp_raw_controls": True,
+         "materialize_tensors": 1, "visualize": 1, "debug_cells": 1},
+        P.NAV2_BRINGUP_CRITICS, P.NAV2_BRINGUP_CRITIC_PARAMS, robot_radius=0.22,
+        inflation={"cost_scaling_factor": 3.0, "inflation_radius": 0.70})
+    cells = build_map("blocks", seed=6)
+    pair = Pair(cfg, cells)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    drive(pair, path, (10.0, 10.0, 0.0), (0.2, 0.0, 0.1), cycles=8, label=f"delay-{model}")
+    pair.close()
+
+
+def test_speed_limit_reset_and_reconfigure():
+    """Optimizer::setSpeedLimit (optimizer.cpp:691-719), reset(), and a dynamic parameter update that
+    changes batch_size / time_steps (ParametersHandler post-callback -> reset, optimizer.cpp:155)."""
+    cfg = P.nav2_bringup_config()
+    cells = build_map("blocks", seed=7)
+    pair = Pair(cfg, cells)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    inp = nb.CycleInput(pose=(10.0, 10.0, 0.0), speed=(0.3, 0.0, 0.0), path=path, goal_checker_xy_tolerance=0.25)
+    for _ in range(3):
+        g, c = pair.step(inp)
+        assert_cycle_close(g, c, label="before limit")
+        pair.gpu.setState(pair.cpu.getState()); pair.gpu.setControlSequence(pair.cpu.getOptimalControlSequence())
+    for eng in (pair.gpu, pair.cpu):
+        eng.setSpeedLimit(40.0, True)                      # 40 % of the maximum speeds
+    for _ in range(4):
+        g, c = pair.step(inp)
+        assert_cycle_close(g, c, label="limited")
+        assert np.all(g.control_sequence[0, 1:] <= 0.5 * 0.4 + 1e-6)
+        pair.gpu.setState(pair.cpu.getState()); pair.gpu.setControlSequence(pair.cpu.getOptimalControlSequence())
+    for eng in (pair.gpu, pair.cpu):
+        eng.setSpeedLimit(0.0, False)                      # NO_SPEED_LIMIT
+        eng.reset()
+    assert np.all(pair.gpu.getOptimalControlSequence() == 0.0)
+    # the noise tensors were injected, so they survive reset() on both sides
+    g, c = pair.step(inp)
+    assert_cycle_close(g, c, label="after reset")
+    # dynamic reconfiguration: new shapes, fresh device buffers
+    cfg2 = P.nav2_bringup_config(batch_size=768, time_steps=40)
+    pair.gpu.setConfig(cfg2)
+    cpu2 = type(pair.cpu)(cfg2)
+    cpu2.setCostmap(cells, 0.05, 0.0, 0.0)
+    nvx, nvy, nwz = S.seeded_noise(768, 40, (cfg2.vx_std, cfg2.vy_std, cfg2.wz_std), seed=9)
+    pair.gpu.setNoise(nvx, nvy, nwz)
+    cpu2.setNoise(nvx, nvy, nwz)
+    g = pair.gpu.evalControl(inp)
+    c = cpu2.evalControl(inp)
+    assert g.control_sequence.shape == (3, 40)
+    assert_cycle_close(g, c, label="reconfigured")
+    cpu2.shutdown()
+    pair.close()
+
+
+def test_fallback_retries_and_no_valid_control():
+    """fallback() (optimizer.cpp:281-298): every trajectory collides -> reset, retry, NoValidControl after
+    retry_attempt_limit; the next call on a free map works again."""
+    cfg = P.make_config({"batch_size": 512, "time_steps": 30, "retry_attempt_limit": 2, "controller_frequency": 20.0},
+                        ["ConstraintCritic", "CostCritic", "PreferForwardCritic"], robot_radius=0.1)
+    lethal = np.full((100, 100), 254, dtype=np.uint8)
+    free = np.zeros((100, 100), dtype=np.uint8)
+    pair = Pair(cfg, lethal, resolution=0.1)
+    path = np.stack([np.linspace(5, 6, 10), np.full(10, 5.0), np.zeros(10)], axis=1)
+    inp = nb.CycleInput(pose=(5.0, 5.0, 0.0), speed=(0.0, 0.0, 0.0), path=path)
+    g, c = pair.step(inp, raise_on_failure=False)
+    assert g.status == c.status == capi.MPPI_ERR_NO_VALID_CONTROL
+    assert g.retries == c.retries == 2 and g.fail_flag and c.fail_flag
+    with pytest.raises(nb.NoValidControl):
+        pair.gpu.evalControl(inp)
+    for eng in (pair.gpu, pair.cpu):
+        eng.setCostmap(free, 0.1, 0.0, 0.0)
+    g, c = pair.step(inp)
+    assert g.status == 0 and not g.fail_flag
+    assert_cycle_close(g, c, label="recovered")
+    pair.close()
+
+
+def test_validator_soft_reset():
+    """OptimalTrajectoryValidator (optimal_trajectory_validator.hpp:117-158): an inscribed cell right in front of
+    the robot with no collision critic configured -> SOFT_RESET -> retries -> NoValidControl, same as the oracle."""
+    cfg = P.make_config({"batch_size": 256, "time_steps": 30, "retry_attempt_limit": 1, "controller_frequency": 20.0},
+                        ["ConstraintCritic", "PreferForwardCritic", "PathFollowCritic"], robot_radius=0.1)
+    cells = np.zeros((100, 100), dtype=np.uint8)
+    cells[48:53, 50:60] = 253
+    pair = Pair(cfg, cells, resolution=0.1)
+    path = np.stack([np.linspace(5, 8, 40), np.full(40, 5.0), np.zeros(40)], axis=1)
+    inp = nb.CycleInput(pose=(4.9, 5.0, 0.0), speed=(0.3, 0.0, 0.0), path=path)
+    g, c = pair.step(inp, raise_on_failure=False)
+    assert g.status == c.status
+    assert g.validation == c.validation
+    assert g.retries == c.retries
+    pair.close()
+
+
+def test_philox_noise_statistics_and_shard_invariance():
+    """NoiseGenerator::generateNoisedControls replacement: N(0, sigma^2) per axis (the reference's own check is
+    |noise| bounds at sigma = 0.1, noise_generator_test.cpp:97-100), zero vy for non-holonomic models, and the
+    same global tensor regardless of how the batch is sharded (counter = global trajectory index)."""
+    cfg = P.nav2_bringup_config(batch_size=4096, time_steps=56)
+    opt = nb.Optimizer(cfg)
+    nvx, nvy, nwz = (opt.getTensor(t) for t in (capi.TENSOR_NOISE_VX, capi.TENSOR_NOISE_VY, capi.TENSOR_NOISE_WZ))
+    assert abs(nvx.mean()) < 3e-3 and abs(nvx.std() - 0.2) < 3e-3
+    assert abs(nwz.mean()) < 6e-3 and abs(nwz.std() - 0.4) < 6e-3
+    assert np.all(nvy == 0.0)
+    assert abs(np.corrcoef(nvx.ravel(), nwz.ravel())[0, 1]) < 0.01
+    assert np.abs(nvx).max() < 0.2 * 6.5
+    halves = []
+    for rank in range(2):
+        c2 = P.nav2_bringup_config(batch_size=4096, time_steps=56, shard_world=2, shard_rank=rank)
+        o2 = nb.Optimizer(c2)
+        halves.append(o2.getTensor(capi.TENSOR_NOISE_VX))
+        o2.shutdown()
+    assert np.array_equal(np.concatenate(halves, axis=1), nvx)
+    opt.reset()                                   # reset() draws a fresh tensor (noise_generator.cpp:77-96)
+    assert not np.array_equal(opt.getTensor(capi.TENSOR_NOISE_VX), nvx)
+    opt.shutdown()
+
+
+def test_fleet_matches_single_robot_handles():
+    """Fleet mode: n_robots independent robots in one handle give exactly what separate handles give."""
+    R = 3
+    cfgR = P.nav2_bringup_config(n_robots=R, batch_size=1000)
+    cfg1 = P.nav2_bringup_config(batch_size=1000)
+    fleet = nb.Optimizer(cfgR)
+    singles = [nb.Optimizer(cfg1) for _ in range(R)]
+    inputs = []
+    for r in range(R):
+        cells = build_map("blocks", seed=20 + r, size=200, pose=(5.0, 5.0))
+        nvx, nvy, nwz = S.seeded_noise(1000, 56, (0.2, 0.2, 0.4), seed=100 + r)
+        fleet.setCostmap(cells, 0.05, 0.0, 0.0, robot=r)
+        fleet.setNoise(nvx, nvy, nwz, robot=r)
+        singles[r].setCostmap(cells, 0.05, 0.0, 0.0)
+        singles[r].setNoise(nvx, nvy, nwz)
+        path = S.arc_path((5.0, 5.0, 0.1 * r), n_points=80, curvature=0.1 * (r - 1))
+        inputs.append(nb.CycleInput(pose=(5.0, 5.0, 0.1 * r), speed=(0.1 * r, 0.0, 0.0), path=path, goal_checker_xy_tolerance=0.25))
+    for cycle in range(3):
+        res = fleet.evalControl(inputs)
+        for r in range(R):
+            one = singles[r].evalControl(inputs[r])
+            np.testing.assert_array_equal(res[r].control_sequence, one.control_sequence, err_msg=f"robot {r} cycle {cycle}")
+            assert res[r].cmd == one.cmd
+    fleet.shutdown()
+    for s_ in singles:
+        s_.shutdown()
