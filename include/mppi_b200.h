@@ -237,7 +237,7 @@ typedef enum MppiTensor
   MPPI_TENSOR_COST_CELLS = 15,      /* uint32[n_s * B]: CostCritic cell index per strided sample, 0xFFFFFFFF off-map, 0xFFFFFFFE not visited (debug_cells) */
   MPPI_TENSOR_OBSTACLE_CELLS = 16,  /* uint32[T * B]: ObstaclesCritic cell index per step, same sentinels (debug_cells) */
   MPPI_TENSOR_SOFTMAX = 17,         /* float[B]: unnormalised softmax weights exp(-(c - min)/temperature) */
-  MPPI_TENSOR_PHASE_CLOCKS = 18     /* int64[16 * 32]: SM clock at the phase boundaries of the fused kernel, per cluster rank
+  MPPI_TENSOR_PHASE_CLOCKS = 18     /* int64[16 * 16 * 32]: SM clock at the phase boundaries of the fused kernel, per cluster rank and warp
                                        (tracing; enabled by the environment variable MPPI_B200_PHASE_CLOCKS=1) */
 } MppiTensor;
 
@@ -383,6 +383,15 @@ void * mppi_stream(MppiHandle * h);
  * collectives against); NULL restores the handle's own stream. */
 int mppi_set_stream(MppiHandle * h, void * cuda_stream);
 int mppi_device_synchronize(MppiHandle * h);
+
+/* Device self-test (no reference equivalent).  The fused kernel divides by the costmap resolution
+ * and takes square roots with straight-line sequences that must equal the IEEE operators the
+ * reference uses (CostCritic::worldToMapFloat, cost_critic.hpp:100-113; utils.hpp:307-312).  Runs
+ * both on n host operand pairs (a[i] / b[i], sqrt(|a[i]|)) and counts results that differ from `/`
+ * and sqrtf (must be 0) and operands the sequences decline (handled by the operators themselves).
+ * Errors are reported through mppi_last_error(NULL). */
+int mppi_selftest_exact_math(
+  const float * a, const float * b, int n, unsigned int * mismatches, unsigned int * flagged);
 
 /* ---- batch sharding across GPUs: one process per GPU, collectives by the caller ---- */
 

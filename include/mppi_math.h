@@ -39,14 +39,12 @@
 /* sin and cos of x, ~1 ulp for |x| < ~1e4, deterministic everywhere (NaN for non-finite). */
 MPPI_HD void mppi_sincosf(float x, float * s_out, float * c_out)
 {
-  if (!(fabsf(x) < 1.0e8f)) {  /* huge, inf or nan: no meaningful heading; propagate NaN */
-    const float bad = x - x;  /* 0 for finite, NaN otherwise */
-    *s_out = bad;
-    *c_out = 1.0f + bad;
-    return;
-  }
-  const float k = rintf(x * MPPI_2_OVER_PI);
-  float r = fmaf(-k, MPPI_PIO2_HI, x);
+  /* huge, inf or nan: no meaningful heading; propagate NaN.  Selected at the end instead of an early
+   * return so the routine is straight-line code (the GPU interleaves several calls for latency). */
+  const bool ok = fabsf(x) < 1.0e8f;
+  const float xs = ok ? x : 0.0f;
+  const float k = rintf(xs * MPPI_2_OVER_PI);
+  float r = fmaf(-k, MPPI_PIO2_HI, xs);
   r = fmaf(-k, MPPI_PIO2_MID, r);
   r = fmaf(-k, MPPI_PIO2_LO, r);
   const int q = static_cast<int>(k) & 3;
@@ -61,8 +59,11 @@ MPPI_HD void mppi_sincosf(float x, float * s_out, float * c_out)
   /* quadrant: q odd swaps sin/cos; sin is negated for q = 2, 3 and cos for q = 1, 2 */
   const float a = (q & 1) ? cs : sn;
   const float b = (q & 1) ? sn : cs;
-  *s_out = (q & 2) ? -a : a;
-  *c_out = ((q + 1) & 2) ? -b : b;
+  const float s = (q & 2) ? -a : a;
+  const float c = ((q + 1) & 2) ? -b : b;
+  const float bad = x - x;  /* 0 for finite, NaN otherwise */
+  *s_out = ok ? s : bad;
+  *c_out = ok ? c : 1.0f + bad;
 }
 
 /* utils.hpp:254-262 normalize_angles (float, Eigen side): fmodf is exact on CPU and GPU. */

@@ -217,6 +217,7 @@ SYMBOLS = {
     "mppi_stream": (_P, [_P]),
     "mppi_set_stream": (C.c_int, [_P, _P]),
     "mppi_device_synchronize": (C.c_int, [_P]),
+    "mppi_selftest_exact_math": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "mppi_shard_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(_P)]),
     "mppi_shard_begin": (C.c_int, [_P, C.POINTER(MppiCycleIn)]),
     "mppi_shard_rollout": (C.c_int, [_P]),

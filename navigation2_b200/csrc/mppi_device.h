@@ -18,6 +18,7 @@
 #define MPPI_MAX_PARTIAL_BLOCKS 296  // 2 x 148 SMs
 #define MPPI_FUSED_G 128        // fused small-batch kernel: trajectories per CTA
 #define MPPI_FUSED_THREADS 512  // 4 roles x MPPI_FUSED_G
+#define MPPI_PHASE_CLOCK_WORDS (MPPI_FUSED_MAX_CLUSTER * (MPPI_FUSED_THREADS / 32) * 32)  // per robot
 #define MPPI_FUSED_MAX_CLUSTER 16
 
 // slots of the per-robot reduction words (int32); the first MPPI_AR1_WORDS are what batch
@@ -181,8 +182,14 @@ struct KArgs
   const float * path;   // [R][4][max_path]: x, y, yaw, integrated distance
   const uint8_t * path_valid;  // [R][max_path]
   DevCycle * cyc;       // [R]
+  // Where an iteration READS its inputs from; the live buffers above are where it WRITES.  They are the same
+  // buffers except on the first iteration of a resident replay (pristine copies: no restore copies needed) and
+  // of a single-launch cycle (the pinned host block, read over PCIe: no H2D copy node ahead of the kernel).
+  const DevCycle * cyc_in;
+  const float * u_in;
+  const float * hist_in;
   const DevStatic * st;
-  long long * phase_clocks;  // [R][MPPI_FUSED_MAX_CLUSTER][32] SM clock at each phase boundary of the fused kernel, or null
+  long long * phase_clocks;  // [R][MPPI_FUSED_MAX_CLUSTER][warps][32] SM clock at each phase boundary of the fused kernel, or null
   uint8_t * out;        // [R][out_stride]
   size_t out_stride;
 };

@@ -41,6 +41,7 @@ struct KSmemF
   uint32_t off_fin;    // finalize scratch, 11 T floats
   uint32_t off_win;    // uint8 costmap window
   int32_t path_cap;
+  int32_t has_lut;   // the obstacle LUT is allocated (ObstaclesCritic configured)
   uint32_t total;
 };
 
@@ -72,5 +73,8 @@ cudaError_t mppi_launch_finalize(const KArgs & a, bool holo, int shard_stage, cu
 cudaError_t mppi_launch_philox(
   float * nvx, float * nvy, float * nwz, int B, int T, int R, int b_offset, uint64_t seed,
   uint32_t epoch, float std_vx, float std_vy, float std_wz, bool holo, cudaStream_t stream);
+
+cudaError_t mppi_launch_selftest_exact_math(
+  const float * a, const float * b, int n, unsigned int * mismatches, unsigned int * flagged, cudaStream_t stream);
 
 #endif  // NAVIGATION2_B200_CSRC_MPPI_KERNELS_H_

@@ -57,3 +57,29 @@ def test_each_critic_matches_oracle_on_random_tensors(critic, model):
         assert_costs_close(gc, cc, label=f"{critic}/{model}/lpl={lpl}")
     g.shutdown()
     c.shutdown()
+
+
+def test_exact_division_and_sqrt_sequences_match_ieee_operators():
+    """The fused kernel's straight-line division / square root against `/` and sqrtf on the
+    device: world-to-map quotients near cell boundaries, random magnitudes, zeros, tiny and huge values."""
+    import ctypes as C
+    from navigation2_b200 import capi
+    lib = capi.load_library()
+    rng = np.random.default_rng(123)
+    n = 1 << 22
+    res = rng.choice(np.array([0.05, 0.1, 0.025, 0.02, 0.2, 1.0 / 3.0, 0.0499999], dtype=np.float32), size=n)
+    cells = rng.integers(0, 4000, size=n).astype(np.float32)
+    # numerators a hair's breadth around exact cell boundaries, plus log-uniform magnitudes
+    a = (cells * res).astype(np.float32)
+    a = np.nextafter(a, np.where(rng.random(n) < 0.5, np.float32(np.inf), np.float32(-np.inf))).astype(np.float32)
+    k = n // 4
+    a[:k] = np.exp(rng.uniform(-40, 40, size=k)).astype(np.float32)
+    res[:k // 2] = np.exp(rng.uniform(-30, 30, size=k // 2)).astype(np.float32)
+    a[k:k + 64] = 0.0
+    a[k + 64:k + 128] = np.float32(1e-30)
+    a[k + 128:k + 192] = np.float32(3e38)
+    mism, flagged = C.c_uint(0), C.c_uint(0)
+    rc = lib.mppi_selftest_exact_math(a.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p), n, C.byref(mism), C.byref(flagged))
+    assert rc == 0, lib.mppi_last_error(None)
+    assert mism.value == 0
+    assert 0 < flagged.value < n // 100      # only the planted extremes are declined
