@@ -333,26 +333,32 @@ def run_ours(args):
     ka_ms, ka_n = opt.kernelTimeMs(reset=True)
     opt.setKernelTiming(False)
 
-    # ---- e2e: the C ABI with HOST buffers.  Every step uploads the costmap (pinned staging ->
-    # cudaMemcpy2DAsync on the side stream) and calls mppi_optimize (H2D cycle block, kernels, D2H of
-    # the command + control sequence + optimal trajectory, host sync).  Timed inside the library with
-    # steady_clock per call (mppi_time_e2e), i.e. what a C++ controller_server thread would see; the
-    # same loop through the Python binding is reported next to it. ----
+    # ---- e2e: the C ABI with HOST buffers, timed inside the library with steady_clock per call (mppi_time_e2e),
+    # i.e. what a C++ controller_server thread sees.  Primary: mppi_optimize_in_place, the reference's own shape of
+    # the call (evalControl reads the costmap where it lies, under the costmap mutex): pack the costmap window +
+    # cycle inputs, ONE H2D copy, ONE kernel, result in mapped pinned memory, host sync.  Also reported: the
+    # two-call sequence (mppi_upload_costmap stages the whole map first) and the same loop through Python. ----
     opt.setResidentCapture(False)
     opt.reset()
-    opt.timeE2E(wl["cells"], wl["resolution"], wl["origin"], inputs, args.warmup)
-    if distributed:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e2e_times = opt.timeE2E(wl["cells"], wl["resolution"], wl["origin"], inputs, args.steps)
-    torch.cuda.synchronize()
+
+    def timed_e2e(in_place):
+        opt.timeE2E(wl["cells"], wl["resolution"], wl["origin"], inputs, args.warmup, in_place=in_place)
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        b0 = opt.h2dByteCount()
+        t = opt.timeE2E(wl["cells"], wl["resolution"], wl["origin"], inputs, args.steps, in_place=in_place)
+        torch.cuda.synchronize()
+        return t, (opt.h2dByteCount() - b0) / args.steps
+
+    two_call_times, two_call_h2d = timed_e2e(False)
+    e2e_times, h2d = timed_e2e(True)
     e2e_total = float(e2e_times.sum())
     py_times = []
+    maps = [(wl["cells"], wl["resolution"], wl["origin"][0], wl["origin"][1])] * R
     for _ in range(min(args.steps, 50)):
         t0 = time.perf_counter()
-        for r in range(R):
-            opt.setCostmap(wl["cells"], wl["resolution"], *wl["origin"], robot=r)
-        opt.evalControl(inputs)
+        opt.evalControl(inputs, costmaps=maps if R > 1 else maps[0])
         py_times.append(time.perf_counter() - t0)
     py_times = np.array(py_times)
     if distributed:
@@ -360,12 +366,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_total = float(t.item())
     e2e_value = world * units_per_step * args.steps / e2e_total
-    n_path = np.asarray(wl["inp"].path).reshape(-1, 3).shape[0]
-    max_path = 256
-    while max_path < n_path:
-        max_path *= 2
-    h2d = R * (wl["cells"].size + 512 + 17 * max_path)       # costmap + DevCycle + path arrays/validity
-    d2h = R * (32 + 6 * T * 4)                               # header + control sequence + optimal trajectory
+    d2h = R * (48 + 6 * T * 4)                               # header + control sequence + optimal trajectory
+    window_misses = opt.windowMissCount()
 
     clocks = sampler.stop() if rank == 0 else None
 
@@ -400,7 +402,11 @@ def run_ours(args):
         "value_hot_l2": world * units_per_step / (float(np.mean(hot_ms)) * 1e-3),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "p50_latency_us": float(np.median(e2e_times) * 1e6), "mean_latency_us": float(np.mean(e2e_times) * 1e6),
-                "timed": "mppi_time_e2e: steady_clock around (mppi_upload_costmap + mppi_optimize) inside the C library",
+                "timed": "mppi_time_e2e: steady_clock around mppi_optimize_in_place (costmap read in the caller's memory) "
+                         "inside the C library",
+                "window_misses": int(window_misses),
+                "two_call": {"p50_latency_us": float(np.median(two_call_times) * 1e6), "h2d_bytes_per_step": int(two_call_h2d),
+                             "timed": "mppi_upload_costmap (whole map staged) + mppi_optimize"},
                 "p50_latency_us_python_binding": float(np.median(py_times) * 1e6)},
         "gpu_launches": int(launches_timed),
         "roofline": roofline,

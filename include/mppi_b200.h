@@ -277,6 +277,7 @@ size_t mppi_sizeof_critic_params(void);
 size_t mppi_sizeof_cycle_in(void);
 size_t mppi_sizeof_cycle_out(void);
 size_t mppi_sizeof_optimizer_state(void);
+size_t mppi_sizeof_costmap_view(void);
 /* InflationLayer::computeCost (nav2_costmap_2d/include/nav2_costmap_2d/inflation_layer.hpp:121-135) */
 uint8_t mppi_inflation_compute_cost(
   double distance_cells, double resolution, double inscribed_radius, double cost_scaling_factor);
@@ -304,8 +305,10 @@ const char * mppi_last_error(const MppiHandle * h);
 /* Replaces the critics' direct reads of Costmap2D::getCharMap()/getOriginX()/getResolution()/
  * getSizeInCells*() (cost_critic.cpp:138-144; nav2_costmap_2d/src/costmap_2d.cpp:265-305).
  * `cells` is row-major uint8, idx = my * size_x + mx (costmap_2d.hpp:231-234).  The bytes are
- * copied to pinned staging and sent with cudaMemcpy2DAsync on a side stream; the next
- * mppi_optimize waits on its event.  Call while holding the costmap mutex, as the reference does
+ * copied to pinned staging (the caller's buffer is free again on return) and sent by pinned
+ * cudaMemcpyAsync: on a side stream right away when the handle runs the general kernels, by the
+ * next mppi_optimize on its own stream — window or whole map, see mppi_optimize_in_place — when
+ * its cycles are a single launch.  Call while holding the costmap mutex, as the reference does
  * (controller.cpp:106-107). */
 int mppi_upload_costmap(
   MppiHandle * h, uint32_t robot, const uint8_t * cells, uint32_t size_x, uint32_t size_y,
@@ -326,6 +329,32 @@ int mppi_generate_noise(MppiHandle * h, uint32_t robot);
  * `in` and `out` are arrays of n_robots.  Host buffers in, host buffers out; H2D/D2H inside.
  * Returns MPPI_OK if the call ran; per-robot results are in out[i].status. */
 int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out);
+
+/* One robot's costmap where it lies in the caller's memory: what a critic sees through
+ * Costmap2D::getCharMap() / getSizeInCellsX() / getResolution() / getOriginX() while it scores
+ * (cost_critic.cpp:138-144).  Row-major uint8, idx = my * size_x + mx. */
+typedef struct MppiCostmapView
+{
+  const uint8_t * cells;
+  uint32_t size_x, size_y;
+  double resolution, origin_x, origin_y;
+} MppiCostmapView;
+
+/* mppi_upload_costmap for every robot + mppi_optimize in one call, the way the reference does it:
+ * evalControl reads the costmap in place, under the costmap mutex the caller holds
+ * (controller.cpp:106-107).  `costmaps` is an array of n_robots views that must stay valid and unchanged
+ * until the call returns.  Knowing the robot pose at the moment it sees the costmap lets the library
+ * send only the cells the trajectories can plausibly reach (a ~10 KB window instead of a 160 KB map
+ * at the reference configuration); the kernel detects a lookup outside that window, commits nothing,
+ * and the cycle is repeated with the whole map (mppi_window_miss_count).  Results are identical to
+ * the two-call sequence. */
+int mppi_optimize_in_place(
+  MppiHandle * h, const MppiCostmapView * costmaps, const MppiCycleIn * in, MppiCycleOut * out);
+/* Cycles that had to be repeated with the whole costmap since the handle was created. */
+uint64_t mppi_window_miss_count(const MppiHandle * h);
+/* Bytes of costmaps, cycle inputs and costmap windows this handle has copied host -> device since it was
+ * created (bench.py derives "h2d_bytes_per_step" from it). */
+uint64_t mppi_h2d_byte_count(const MppiHandle * h);
 
 /* The scoring pass alone, on caller-supplied tensors: CriticManager::evalTrajectoriesScores
  * (critic_manager.cpp:76-121) with CriticData{state, trajectories, path, goal, costs, ...} given
@@ -363,12 +392,14 @@ int mppi_enqueue_score_resident(MppiHandle * h, void * cuda_stream);
 /* mppi_enqueue_resident replays the inputs of the last mppi_optimize; keeping the pristine copies it
  * needs costs three small device copies per cycle, so it is opt-in. */
 int mppi_set_resident_capture(MppiHandle * h, int enabled);
-/* `cycles` back-to-back (mppi_upload_costmap for every robot; mppi_optimize) pairs, each timed with
- * steady_clock on the calling thread: the end-to-end latency of this C ABI with host buffers
- * (H2D costmap + cycle inputs, kernels, D2H result).  per_call_seconds receives `cycles` entries. */
+/* `cycles` back-to-back control cycles, each timed with steady_clock on the calling thread: the
+ * end-to-end latency of this C ABI with host buffers (H2D costmap + cycle inputs, kernels, D2H
+ * result).  in_place = 0: (mppi_upload_costmap for every robot; mppi_optimize) pairs; in_place != 0:
+ * mppi_optimize_in_place with the same costmap for every robot.  per_call_seconds receives `cycles`
+ * entries. */
 int mppi_time_e2e(
   MppiHandle * h, const uint8_t * cells, uint32_t size_x, uint32_t size_y, double resolution, double origin_x,
-  double origin_y, const MppiCycleIn * in, MppiCycleOut * out, int cycles, double * per_call_seconds);
+  double origin_y, const MppiCycleIn * in, MppiCycleOut * out, int cycles, int in_place, double * per_call_seconds);
 /* Kernels launched by this handle since creation (bench.py "gpu_launches"). */
 uint64_t mppi_launch_count(const MppiHandle * h);
 /* CUDA-event time of the dominant (rollout+score) kernel, averaged since the last call with

@@ -130,6 +130,14 @@ class MppiConfig(C.Structure):
     ]
 
 
+class MppiCostmapView(C.Structure):
+    _fields_ = [
+        ("cells", C.POINTER(C.c_uint8)),
+        ("size_x", C.c_uint32), ("size_y", C.c_uint32),
+        ("resolution", C.c_double), ("origin_x", C.c_double), ("origin_y", C.c_double),
+    ]
+
+
 class MppiCycleIn(C.Structure):
     _fields_ = [
         ("pose_x", C.c_double), ("pose_y", C.c_double), ("pose_yaw", C.c_double),
@@ -187,6 +195,7 @@ SYMBOLS = {
     "mppi_sizeof_cycle_in": (C.c_size_t, []),
     "mppi_sizeof_cycle_out": (C.c_size_t, []),
     "mppi_sizeof_optimizer_state": (C.c_size_t, []),
+    "mppi_sizeof_costmap_view": (C.c_size_t, []),
     "mppi_inflation_compute_cost": (C.c_uint8, [C.c_double, C.c_double, C.c_double, C.c_double]),
     "mppi_create": (C.c_int, [C.POINTER(MppiConfig), C.POINTER(_P)]),
     "mppi_destroy": (C.c_int, [_P]),
@@ -209,7 +218,10 @@ SYMBOLS = {
     "mppi_enqueue_score_resident": (C.c_int, [_P, _P]),
     "mppi_set_resident_capture": (C.c_int, [_P, C.c_int]),
     "mppi_time_e2e": (C.c_int, [_P, _U8, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double,
-                                C.POINTER(MppiCycleIn), C.POINTER(MppiCycleOut), C.c_int, C.POINTER(C.c_double)]),
+                                C.POINTER(MppiCycleIn), C.POINTER(MppiCycleOut), C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "mppi_optimize_in_place": (C.c_int, [_P, C.POINTER(MppiCostmapView), C.POINTER(MppiCycleIn), C.POINTER(MppiCycleOut)]),
+    "mppi_window_miss_count": (C.c_uint64, [_P]),
+    "mppi_h2d_byte_count": (C.c_uint64, [_P]),
     "mppi_launch_count": (C.c_uint64, [_P]),
     "mppi_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "mppi_kernel_time_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -262,6 +274,7 @@ def check_abi(lib: C.CDLL | None = None) -> None:
         (lib.mppi_sizeof_cycle_in(), C.sizeof(MppiCycleIn), "MppiCycleIn"),
         (lib.mppi_sizeof_cycle_out(), C.sizeof(MppiCycleOut), "MppiCycleOut"),
         (lib.mppi_sizeof_optimizer_state(), C.sizeof(MppiOptimizerState), "MppiOptimizerState"),
+        (lib.mppi_sizeof_costmap_view(), C.sizeof(MppiCostmapView), "MppiCostmapView"),
     ]
     for native, here, name in pairs:
         if native != here:

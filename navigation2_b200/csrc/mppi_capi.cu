@@ -46,8 +46,13 @@ struct HostRobot
   uint32_t noise_epoch = 0;
   cudaEvent_t stage_event = nullptr;   // completion of the last H2D copy out of this robot's staging slab
   bool stage_pending = false;
-  bool device_stale = false;     // the pinned slab is newer than the device copy
+  bool device_stale = false;     // the host-side map is newer than the device copy
   size_t map_bytes = 0;          // pitch * size_y
+  // where the host reads this robot's cells from (path validity, window packets): the staging slab after
+  // mppi_upload_costmap, the caller's own buffer during mppi_optimize_in_place
+  const uint8_t * map_src = nullptr;
+  uint32_t map_src_pitch = 0;
+  bool staged_current = false;   // the staging slab holds the costmap of the current cycle
 };
 
 #define CU_CHECK(h, call) \
@@ -113,6 +118,14 @@ struct MppiHandle
   // h_map_stage / d_map and h_cycle_block / d_cycle_block point into them, so a single-launch cycle moves the
   // freshly written costmap and the cycle block host -> device with ONE copy ahead of ONE kernel.
   uint8_t * h_arena = nullptr, * d_arena = nullptr;
+  // ... followed by the window packets of a single-launch cycle (tightly packed, DevCycle::win_packet_off)
+  uint8_t * h_packets = nullptr, * d_packets = nullptr;
+  size_t packets_capacity = 0;
+  size_t packets_used = 0;
+  int window_half_override = 0;   // MPPI_B200_WINDOW_HALF=<cells>: shrink the staged window (tests force window misses)
+  uint64_t h2d_bytes = 0;         // bytes of costmaps, cycle blocks and window packets copied host -> device so far
+  uint64_t window_misses = 0;     // window-only attempts that had to be repeated with the whole map
+  bool window_only = true;        // MPPI_B200_NO_WINDOW_ONLY=1: single-launch cycles upload the whole map (A/B measurements)
   uint8_t * h_cycle_block = nullptr;
   size_t cycle_block_bytes = 0;
   uint8_t * h_out = nullptr;
@@ -433,6 +446,8 @@ int allocate(MppiHandle * h)
     }
   }
   if (const char * e = std::getenv("MPPI_B200_NO_SINGLE_COPY"); e && e[0] == '1') {h->single_copy = false;}
+  if (const char * e = std::getenv("MPPI_B200_NO_WINDOW_ONLY"); e && e[0] == '1') {h->window_only = false;}
+  if (const char * e = std::getenv("MPPI_B200_WINDOW_HALF"); e && std::atoi(e) > 0) {h->window_half_override = std::atoi(e);}
   if (const char * e = std::getenv("MPPI_B200_PHASE_CLOCKS"); e && e[0] == '1') {
     CU_CHECK(h, cudaMalloc(&h->d_phase_clocks, R * MPPI_PHASE_CLOCK_WORDS * sizeof(long long)));
     CU_CHECK(h, cudaMemset(h->d_phase_clocks, 0, R * MPPI_PHASE_CLOCK_WORDS * sizeof(long long)));
@@ -496,7 +511,9 @@ int ensure_arena(MppiHandle * h, size_t need_stride, int need_path)
   const size_t block = cycle_block_size(h->R, cap);
   if (!same_shape) {
     uint8_t * nh = nullptr, * nd = nullptr;
-    const size_t total = stride * h->R + block;
+    // window packets only where single-launch cycles can happen (all clusters in one wave of the SMs)
+    const size_t packets = h->R <= 148 ? static_cast<size_t>(h->R) * MPPI_MAX_WINDOW_BYTES : 0;
+    const size_t total = stride * h->R + block + packets;
     CU_CHECK(h, cudaMallocHost(&nh, total));
     std::memset(nh, 0, total);
     if (cudaMalloc(&nd, total) != cudaSuccess || cudaMemset(nd, 0, total) != cudaSuccess) {
@@ -509,6 +526,7 @@ int ensure_arena(MppiHandle * h, size_t need_stride, int need_path)
       HostRobot & rb = h->robots[r];
       if (rb.map_valid && rb.map_host) {
         std::memcpy(nh + stride * r, rb.map_host, rb.map_bytes);
+        if (rb.map_src == rb.map_host) {rb.map_src = nh + stride * r;}
         rb.map_host = nh + stride * r;
         rb.device_stale = true;
       }
@@ -523,6 +541,9 @@ int ensure_arena(MppiHandle * h, size_t need_stride, int need_path)
     h->h_map_stage = nh; h->d_map = nd;
     h->h_cycle_block = nh + stride * h->R;
     h->d_cycle_block = nd + stride * h->R;
+    h->h_packets = h->h_cycle_block + block;
+    h->d_packets = h->d_cycle_block + block;
+    h->packets_capacity = packets;
   }
   if (h->d_cycle_saved) {cudaFree(h->d_cycle_saved); h->d_cycle_saved = nullptr;}
   CU_CHECK(h, cudaMalloc(&h->d_cycle_saved, block));
@@ -661,7 +682,7 @@ int prepare_robot(MppiHandle * h, int r, const MppiCycleIn & in, int preset_furt
       const unsigned int mx = static_cast<unsigned int>((wx - rb.origin_x) / rb.resolution);
       const unsigned int my = static_cast<unsigned int>((wy - rb.origin_y) / rb.resolution);
       if (mx < rb.size_x && my < rb.size_y) {
-        const uint8_t cost = rb.map_host[static_cast<size_t>(my) * rb.pitch + mx];
+        const uint8_t cost = rb.map_src[static_cast<size_t>(my) * rb.map_src_pitch + mx];
         if (cost == 254 || cost == 253) {
           ok = false;
         } else if (cost == 255) {
@@ -738,7 +759,8 @@ int prepare_robot(MppiHandle * h, int r, const MppiCycleIn & in, int preset_furt
           std::fabs(static_cast<double>(h->c_vx_min)), h->holo ? static_cast<double>(h->c_vy) : 0.0});
     const double reach = reach_v * h->T * c.model_dt * 1.25 + c.circumscribed_radius + 4.0 * rb.resolution;
     int half = static_cast<int>(std::ceil(reach / rb.resolution));
-    half = std::min(std::max(half, 8), 96);
+    half = std::min(std::max(half, 8), MPPI_MAX_WINDOW_HALF);
+    if (h->window_half_override > 0) {half = std::min(h->window_half_override, MPPI_MAX_WINDOW_HALF);}
     const int cx = static_cast<int>(std::floor((in.pose_x - rb.origin_x) / rb.resolution));
     const int cyy = static_cast<int>(std::floor((in.pose_y - rb.origin_y) / rb.resolution));
     int x0 = std::max(0, cx - half) & ~15;
@@ -779,6 +801,7 @@ KArgs make_args(MppiHandle * h)
   a.red = h->d_red; a.partials = h->d_partials;
   a.ar2_slot = h->d_slot; a.ar2_all = h->d_slot_all;
   a.costmap = h->d_map; a.map_stride = h->map_stride;
+  a.win_packets = h->d_packets; a.map_resident = 1;
   a.path = reinterpret_cast<const float *>(h->d_cycle_block + sizeof(DevCycle) * h->R);
   a.path_valid = h->d_cycle_block + sizeof(DevCycle) * h->R + sizeof(float) * 4 * h->max_path * h->R;
   a.cyc = reinterpret_cast<DevCycle *>(h->d_cycle_block);
@@ -859,7 +882,10 @@ LaunchPlan make_plan(MppiHandle * h)
     // and go through the general thread-per-trajectory kernels with a (blocks, robots) grid.
     const bool one_wave = static_cast<long long>(cs) * h->R <= 148;
     p.cluster_size = cs;
-    p.sm_f = mppi_smem_layout_f(h->T, h->holo, p.path_cap, static_cast<int>(h->cfg.n_critics) + 3, obstacles, win_bytes);
+    // the fused kernel copies the path arrays 16 bytes at a time: capacity rounded up to 16 points (max_path is a
+    // power of two >= 256, the cycle block is zero-initialised, entries past n_path are never read as path points)
+    const int fused_cap = std::min(h->max_path, (p.path_cap + 15) & ~15);
+    p.sm_f = mppi_smem_layout_f(h->T, h->holo, fused_cap, static_cast<int>(h->cfg.n_critics) + 3, obstacles, win_bytes);
     if (p.sm_f.total <= 227u * 1024u) {
       const uint64_t key = (static_cast<uint64_t>(p.sm_f.total) << 8) | static_cast<uint64_t>(cs);
       if (h->fused_checked_key != key) {
@@ -880,9 +906,11 @@ enum class CycleSource
 };
 
 int enqueue_iterations(
-  MppiHandle * h, cudaStream_t stream, const LaunchPlan & plan, bool fresh_costs = false, CycleSource source = CycleSource::LIVE)
+  MppiHandle * h, cudaStream_t stream, const LaunchPlan & plan, bool fresh_costs = false, CycleSource source = CycleSource::LIVE,
+  bool window_only = false)
 {
   KArgs a = make_args(h);
+  a.map_resident = window_only ? 0 : 1;
   const KArgs live = a;
   const int iters = static_cast<int>(h->cfg.iteration_count);
   // the path arrays never change within a cycle: they are read from the source block by every iteration
@@ -966,6 +994,7 @@ uint64_t plan_key(const MppiHandle * h, const LaunchPlan & p)
 int upload_cycle_block(MppiHandle * h, cudaStream_t stream)
 {
   CU_CHECK(h, cudaMemcpyAsync(h->d_cycle_block, h->h_cycle_block, h->cycle_block_bytes, cudaMemcpyHostToDevice, stream));
+  h->h2d_bytes += h->cycle_block_bytes;
   return MPPI_OK;
 }
 
@@ -978,6 +1007,7 @@ int upload_stale_maps(MppiHandle * h)
     if (!rb.device_stale || !rb.map_valid) {continue;}
     CU_CHECK(h, cudaMemcpyAsync(
         h->d_map + h->map_stride * r, h->h_map_stage + h->map_stride * r, rb.map_bytes, cudaMemcpyHostToDevice, h->side));
+    h->h2d_bytes += rb.map_bytes;
     CU_CHECK(h, cudaEventRecord(rb.stage_event, h->side));
     rb.stage_pending = true;
     rb.device_stale = false;
@@ -992,6 +1022,40 @@ int upload_stale_maps(MppiHandle * h)
 
 // Single-launch cycles: everything the kernel needs from the host in as few copies as possible on `stream`.
 // With one robot the stale costmap slab and the cycle block are adjacent in the arena: one copy.
+// Window-only cycles: the rows of each robot's costmap window, packed behind the cycle block (one copy for both).
+int fill_window_packets(MppiHandle * h)
+{
+  size_t off = 0;
+  for (int r = 0; r < h->R; ++r) {
+    HostRobot & rb = h->robots[r];
+    DevCycle & cy = *h->hcyc(r);
+    cy.win_packet_off = static_cast<uint32_t>(off);
+    if (!cy.run || cy.win_w <= 0 || cy.win_h <= 0) {continue;}
+    const size_t bytes = static_cast<size_t>(cy.win_w) * cy.win_h;
+    if (off + bytes > h->packets_capacity) {h->error = "window packets overflow"; return MPPI_ERR_UNSUPPORTED;}
+    uint8_t * dst = h->h_packets + off;
+    // the window's right edge is rounded up to 16 cells and may run past size_x into the row padding
+    const int copy_w = std::min<int>(cy.win_w, static_cast<int>(rb.size_x) - cy.win_x0);
+    for (int row = 0; row < cy.win_h; ++row) {
+      const uint8_t * src = rb.map_src + static_cast<size_t>(cy.win_y0 + row) * rb.map_src_pitch + cy.win_x0;
+      std::memcpy(dst + static_cast<size_t>(row) * cy.win_w, src, copy_w);
+      if (copy_w < cy.win_w) {std::memset(dst + static_cast<size_t>(row) * cy.win_w + copy_w, 0, cy.win_w - copy_w);}
+    }
+    off += bytes;
+  }
+  h->packets_used = off;
+  return MPPI_OK;
+}
+
+int upload_cycle_and_packets(MppiHandle * h, cudaStream_t stream)
+{
+  const size_t block_off = h->map_stride * h->R;
+  CU_CHECK(h, cudaMemcpyAsync(
+      h->d_arena + block_off, h->h_arena + block_off, h->cycle_block_bytes + h->packets_used, cudaMemcpyHostToDevice, stream));
+  h->h2d_bytes += h->cycle_block_bytes + h->packets_used;
+  return MPPI_OK;
+}
+
 int upload_arena(MppiHandle * h, cudaStream_t stream)
 {
   const size_t block_off = h->map_stride * h->R;
@@ -1000,6 +1064,7 @@ int upload_arena(MppiHandle * h, cudaStream_t stream)
     const size_t from = (rb.device_stale && rb.map_valid) ? 0 : block_off;
     CU_CHECK(h, cudaMemcpyAsync(
         h->d_arena + from, h->h_arena + from, block_off + h->cycle_block_bytes - from, cudaMemcpyHostToDevice, stream));
+    h->h2d_bytes += block_off + h->cycle_block_bytes - from;
     rb.device_stale = false;
     return MPPI_OK;
   }
@@ -1008,9 +1073,11 @@ int upload_arena(MppiHandle * h, cudaStream_t stream)
     if (!rb.device_stale || !rb.map_valid) {continue;}
     CU_CHECK(h, cudaMemcpyAsync(
         h->d_arena + h->map_stride * r, h->h_arena + h->map_stride * r, rb.map_bytes, cudaMemcpyHostToDevice, stream));
+    h->h2d_bytes += rb.map_bytes;
     rb.device_stale = false;
   }
   CU_CHECK(h, cudaMemcpyAsync(h->d_arena + block_off, h->h_arena + block_off, h->cycle_block_bytes, cudaMemcpyHostToDevice, stream));
+  h->h2d_bytes += h->cycle_block_bytes;
   return MPPI_OK;
 }
 
@@ -1237,15 +1304,11 @@ int mppi_set_speed_limit(MppiHandle * h, double speed_limit, int percentage)
   return MPPI_OK;
 }
 
-int mppi_upload_costmap(
+// Copies a costmap into the robot's pinned staging slab (16-byte-pitched rows) and makes it the host-side source.
+int stage_map(
   MppiHandle * h, uint32_t robot, const uint8_t * cells, uint32_t size_x, uint32_t size_y,
   double resolution, double origin_x, double origin_y)
 {
-  if (!h || !cells || robot >= static_cast<uint32_t>(h->R) || size_x == 0 || size_y == 0 || !(resolution > 0.0)) {
-    if (h) {h->error = "bad costmap arguments";}
-    return MPPI_ERR_INVALID_ARGUMENT;
-  }
-  const auto ht0 = std::chrono::steady_clock::now();
   const uint32_t pitch = (size_x + 15u) & ~15u;
   const size_t need = static_cast<size_t>(pitch) * size_y;
   if (need > h->map_stride) {
@@ -1268,17 +1331,34 @@ int mppi_upload_costmap(
     }
   }
   rb.map_host = stage;
+  rb.staged_current = true;
+  rb.map_src = stage; rb.map_src_pitch = pitch;
   rb.size_x = size_x; rb.size_y = size_y; rb.pitch = pitch;
   rb.resolution = resolution; rb.origin_x = origin_x; rb.origin_y = origin_y;
   rb.map_valid = true;
   rb.map_bytes = need;
   rb.device_stale = true;
+  return MPPI_OK;
+}
+
+int mppi_upload_costmap(
+  MppiHandle * h, uint32_t robot, const uint8_t * cells, uint32_t size_x, uint32_t size_y,
+  double resolution, double origin_x, double origin_y)
+{
+  if (!h || !cells || robot >= static_cast<uint32_t>(h->R) || size_x == 0 || size_y == 0 || !(resolution > 0.0)) {
+    if (h) {h->error = "bad costmap arguments";}
+    return MPPI_ERR_INVALID_ARGUMENT;
+  }
+  const auto ht0 = std::chrono::steady_clock::now();
+  int rc = stage_map(h, robot, cells, size_x, size_y, resolution, origin_x, origin_y);
+  if (rc != MPPI_OK) {return rc;}
   // General path: pinned cudaMemcpyAsync on the side stream right away, overlapping the host-side preparation of
   // the cycle; consumers wait on map_event.  A handle whose cycles are single-launch (fused) defers it:
-  // mppi_optimize then moves the map and the cycle block, adjacent in the arena, with one copy on its own stream
-  // ahead of the one kernel (two copies on two streams plus an event wait cost ~15 us more per cycle, measured).
+  // mppi_optimize then sends what the kernel needs with ONE copy on its own stream ahead of the ONE kernel —
+  // the costmap window next to the cycle block, or the whole map next to it (two copies on two streams plus an
+  // event wait cost ~15 us more per cycle, measured).
   if (!h->defer_map_upload) {
-    int rc = upload_stale_maps(h);
+    rc = upload_stale_maps(h);
     if (rc != MPPI_OK) {return rc;}
   }
   if (h->host_timers) {h->ht[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - ht0).count();}
@@ -1311,9 +1391,39 @@ int mppi_generate_noise(MppiHandle * h, uint32_t robot)
   return MPPI_OK;
 }
 
+namespace
+{
+int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycleIn * in, MppiCycleOut * out);
+}
+
 int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
 {
   if (!h || !in || !out) {return MPPI_ERR_INVALID_ARGUMENT;}
+  return optimize_impl(h, nullptr, in, out);
+}
+
+int mppi_optimize_in_place(MppiHandle * h, const MppiCostmapView * costmaps, const MppiCycleIn * in, MppiCycleOut * out)
+{
+  if (!h || !costmaps || !in || !out) {return MPPI_ERR_INVALID_ARGUMENT;}
+  for (int r = 0; r < h->R; ++r) {
+    const MppiCostmapView & v = costmaps[r];
+    if (!v.cells || v.size_x == 0 || v.size_y == 0 || !(v.resolution > 0.0)) {
+      h->error = "bad costmap arguments";
+      return MPPI_ERR_INVALID_ARGUMENT;
+    }
+  }
+  const int rc = optimize_impl(h, costmaps, in, out);
+  // the caller's buffers are only borrowed for the duration of the call
+  for (auto & rb : h->robots) {
+    if (rb.map_src != rb.map_host) {rb.map_src = rb.map_host; rb.map_src_pitch = rb.pitch; rb.map_valid = rb.map_host != nullptr && rb.staged_current;}
+  }
+  return rc;
+}
+
+namespace
+{
+int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycleIn * in, MppiCycleOut * out)
+{
   if (h->cfg.shard_world != 1) {
     h->error = "mppi_optimize on a sharded handle: use the mppi_shard_* phases";
     return MPPI_ERR_UNSUPPORTED;
@@ -1340,6 +1450,27 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
       }
     };
   clk::time_point tp = clk::now();
+  if (views) {
+    // mppi_optimize_in_place: the costmaps are read where they lie (path validity, window packets); they are
+    // staged and uploaded whole only if this cycle turns out to need more than the window
+    for (int r = 0; r < h->R; ++r) {
+      const MppiCostmapView & v = views[r];
+      HostRobot & rb = h->robots[r];
+      const uint32_t pitch = (v.size_x + 15u) & ~15u;
+      const size_t need = static_cast<size_t>(pitch) * v.size_y;
+      if (need > h->map_stride) {
+        rc = ensure_arena(h, need, h->max_path);
+        if (rc != MPPI_OK) {return rc;}
+      }
+      rb.size_x = v.size_x; rb.size_y = v.size_y; rb.pitch = pitch;
+      rb.resolution = v.resolution; rb.origin_x = v.origin_x; rb.origin_y = v.origin_y;
+      rb.map_bytes = need;
+      rb.map_src = v.cells; rb.map_src_pitch = v.size_x;
+      rb.map_valid = true;
+      rb.device_stale = true;
+      rb.staged_current = false;
+    }
+  }
   for (int r = 0; r < h->R; ++r) {
     out[r].retries = 0;
     out[r].status = MPPI_OK;
@@ -1349,22 +1480,39 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
   tick(1, tp);
   const LaunchPlan plan = make_plan(h);
   tick(2, tp);
+  // every consumer but the window-only launch needs the whole map on the device: stage what was only borrowed
+  auto stage_borrowed = [&]() -> int {
+      for (int r = 0; views && r < h->R; ++r) {
+        if (h->robots[r].staged_current) {continue;}
+        const MppiCostmapView & v = views[r];
+        const int src = stage_map(h, static_cast<uint32_t>(r), v.cells, v.size_x, v.size_y, v.resolution, v.origin_x, v.origin_y);
+        if (src != MPPI_OK) {return src;}
+      }
+      return MPPI_OK;
+    };
   bool first = true;
+  bool force_resident = false;  // a window-only attempt missed: same attempt again with the whole map
   while (true) {
     // One attempt = H2D of the cycle block, the optimize() iterations, D2H of the result block.  The
     // common case (first attempt, own stream, no per-kernel timing) replays a captured CUDA graph:
     // one launch call instead of one per node.  Addresses are fixed; the plan signature keys the cache.
     const bool graphable = h->use_graphs && first && !h->resident_capture && !h->timing && h->stream == h->own_stream;
     const bool single_copy = graphable && plan.fused && h->single_copy;
+    // window-only: ship the rows of the costmap the trajectories can plausibly reach instead of the map (the
+    // kernel reports a lookup outside them and commits nothing; the attempt is then repeated with the whole map)
+    const bool window_only = single_copy && h->window_only && !force_resident && h->cfg.iteration_count == 1 &&
+      h->packets_capacity > 0;
     h->defer_map_upload = single_copy;
-    if (single_copy) {
-      rc = upload_arena(h, h->stream);
+    if (window_only) {
+      rc = fill_window_packets(h);
+      if (rc == MPPI_OK) {rc = upload_cycle_and_packets(h, h->stream);}
     } else {
-      rc = wait_map(h, h->stream);
+      rc = stage_borrowed();
+      if (rc == MPPI_OK) {rc = single_copy ? upload_arena(h, h->stream) : wait_map(h, h->stream);}
     }
     if (rc != MPPI_OK) {return rc;}
     if (graphable) {
-      const uint64_t key = plan_key(h, plan);
+      const uint64_t key = plan_key(h, plan) ^ (window_only ? 0x9E3779B97F4A7C15ull : 0ull) ^ (single_copy ? 0x7F4A7C159E3779B9ull : 0ull);
       cudaGraphExec_t exec = nullptr;
       for (auto & g : h->graphs) {
         if (g.key == key) {exec = g.exec; break;}
@@ -1385,7 +1533,7 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
         }
         // the finalize kernel writes the result block straight into mapped pinned host memory: no D2H node
         if (crc == MPPI_OK) {
-          crc = enqueue_iterations(h, h->stream, plan, true);
+          crc = enqueue_iterations(h, h->stream, plan, true, CycleSource::LIVE, window_only);
         }
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
@@ -1434,6 +1582,19 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
     tick(3, tp);
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     tick(4, tp);
+    if (window_only) {
+      bool missed = false;
+      for (int r = 0; r < h->R; ++r) {
+        const DevOutHeader * hdr = reinterpret_cast<const DevOutHeader *>(h->h_out + static_cast<size_t>(r) * h->out_stride);
+        missed = missed || (h->hcyc(r)->run && hdr->map_miss);
+      }
+      if (missed) {
+        h->window_misses++;
+        force_resident = true;
+        first = true;   // nothing was committed: this is still the first attempt
+        continue;
+      }
+    }
     bool any_retry = false;
     for (int r = 0; r < h->R; ++r) {
       if (!h->hcyc(r)->run) {continue;}  // finished in an earlier attempt
@@ -1449,6 +1610,17 @@ int mppi_optimize(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
   h->have_cycle = h->resident_capture;
   return MPPI_OK;
 }
+}  // namespace
+
+uint64_t mppi_window_miss_count(const MppiHandle * h)
+{
+  return h ? h->window_misses : 0;
+}
+
+uint64_t mppi_h2d_byte_count(const MppiHandle * h)
+{
+  return h ? h->h2d_bytes : 0;
+}
 
 int mppi_set_resident_capture(MppiHandle * h, int enabled)
 {
@@ -1463,9 +1635,19 @@ int mppi_set_resident_capture(MppiHandle * h, int enabled)
 // binding overhead.  per_call_seconds receives `cycles` entries.
 int mppi_time_e2e(
   MppiHandle * h, const uint8_t * cells, uint32_t size_x, uint32_t size_y, double resolution, double origin_x,
-  double origin_y, const MppiCycleIn * in, MppiCycleOut * out, int cycles, double * per_call_seconds)
+  double origin_y, const MppiCycleIn * in, MppiCycleOut * out, int cycles, int in_place, double * per_call_seconds)
 {
   if (!h || !cells || !in || !out || !per_call_seconds || cycles < 1) {return MPPI_ERR_INVALID_ARGUMENT;}
+  if (in_place) {
+    std::vector<MppiCostmapView> views(h->R, MppiCostmapView{cells, size_x, size_y, resolution, origin_x, origin_y});
+    for (int i = 0; i < cycles; ++i) {
+      const auto t0 = std::chrono::steady_clock::now();
+      int rc = mppi_optimize_in_place(h, views.data(), in, out);
+      if (rc != MPPI_OK) {return rc;}
+      per_call_seconds[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return MPPI_OK;
+  }
   // MPPI_B200_E2E_SKIP_UPLOAD=1 (measurement aid): time mppi_optimize alone against the map already on the device
   const char * skip_env = std::getenv("MPPI_B200_E2E_SKIP_UPLOAD");
   const bool skip_upload = skip_env && skip_env[0] == '1';

@@ -183,6 +183,7 @@ size_t mppi_sizeof_critic_params(void) {return sizeof(MppiCriticParams);}
 size_t mppi_sizeof_cycle_in(void) {return sizeof(MppiCycleIn);}
 size_t mppi_sizeof_cycle_out(void) {return sizeof(MppiCycleOut);}
 size_t mppi_sizeof_optimizer_state(void) {return sizeof(MppiOptimizerState);}
+size_t mppi_sizeof_costmap_view(void) {return sizeof(MppiCostmapView);}
 
 // nav2_costmap_2d/include/nav2_costmap_2d/inflation_layer.hpp:121-135
 uint8_t mppi_inflation_compute_cost(

@@ -20,6 +20,8 @@
 #define MPPI_FUSED_THREADS 512  // 4 roles x MPPI_FUSED_G
 #define MPPI_PHASE_CLOCK_WORDS (MPPI_FUSED_MAX_CLUSTER * (MPPI_FUSED_THREADS / 32) * 32)  // per robot
 #define MPPI_FUSED_MAX_CLUSTER 16
+#define MPPI_MAX_WINDOW_HALF 96   // cells either side of the robot staged in shared memory
+#define MPPI_MAX_WINDOW_BYTES (((2 * MPPI_MAX_WINDOW_HALF + 1 + 15 + 15) & ~15) * (2 * MPPI_MAX_WINDOW_HALF + 1))
 
 // slots of the per-robot reduction words (int32); the first MPPI_AR1_WORDS are what batch
 // sharding all-reduces with MAX across ranks
@@ -58,7 +60,7 @@ struct DevCritic
 };
 
 // Static per configuration; uploaded by mppi_create / mppi_set_config.
-struct DevStatic
+struct alignas(16) DevStatic
 {
   DevCritic critics[MPPI_MAX_CRITICS];
   int32_t n_critics;
@@ -94,7 +96,7 @@ struct DevStatic
 
 // Per robot, per evalControl call; uploaded in one H2D copy.  The last fields are updated by the
 // kernels between iterations of the same call.
-struct DevCycle
+struct alignas(16) DevCycle
 {
   double pose_x_d, pose_y_d, pose_yaw_d;
   double origin_x_d, origin_y_d, resolution_d;
@@ -104,6 +106,7 @@ struct DevCycle
   float local_path_length;
   float origin_x_f, origin_y_f, resolution_f;
   uint32_t size_x, size_y, pitch;
+  uint32_t win_packet_off;                  // byte offset of this robot's rows in KArgs::win_packets (window-only cycles)
   int32_t win_x0, win_y0, win_w, win_h;     // costmap window staged in shared memory
   int32_t n_path;
   uint32_t active_mask;                     // bit k: critics[k] passes its enabled / threshold gates
@@ -132,6 +135,9 @@ struct DevOutHeader
   int32_t furthest;
   float cost_min;
   float softmax_sum;
+  int32_t map_miss;   // a lookup fell outside the uploaded costmap window while the full map was not resident:
+                      // nothing was committed (control sequence, filter history); the host uploads the map and reruns
+  int32_t pad[3];
 };
 
 struct KArgs
@@ -179,6 +185,11 @@ struct KArgs
   const float * ar2_all;// [world][R][2 + 3T]
   const uint8_t * costmap;  // [R][map_stride]
   size_t map_stride;
+  // Single-launch cycles upload only the window of the costmap the trajectories can plausibly reach, packed
+  // row by row (win_w x win_h bytes per robot, next to the cycle block: one copy).  map_resident = 0 then:
+  // `costmap` is stale, a lookup outside the window raises DevOutHeader::map_miss instead of reading it.
+  const uint8_t * win_packets;  // robot r's rows start at DevCycle::win_packet_off
+  int32_t map_resident;
   const float * path;   // [R][4][max_path]: x, y, yaw, integrated distance
   const uint8_t * path_valid;  // [R][max_path]
   DevCycle * cyc;       // [R]

@@ -167,8 +167,11 @@ class Optimizer(EngineBase):
     def generateNoise(self, robot: int = 0) -> None:
         _raise_for(self._lib, self._h, self._lib.mppi_generate_noise(self._h, robot))
 
-    def evalControl(self, inputs: CycleInput | Sequence[CycleInput], raise_on_failure: bool = True):
-        """Optimizer::evalControl for every robot; returns one CycleResult (or a list for fleets)."""
+    def evalControl(self, inputs: CycleInput | Sequence[CycleInput], raise_on_failure: bool = True, costmaps=None):
+        """Optimizer::evalControl for every robot; returns one CycleResult (or a list for fleets).
+
+        costmaps: None (the costmaps were sent with setCostmap), or one (cells, resolution, origin_x, origin_y)
+        tuple (a list of them for fleets) read in place for this cycle (mppi_optimize_in_place)."""
         single = isinstance(inputs, CycleInput)
         ins = [inputs] if single else list(inputs)
         if len(ins) != self.R:
@@ -184,7 +187,19 @@ class Optimizer(EngineBase):
             c_out[r].control_vy = u[r, 1].ctypes.data_as(fp)
             c_out[r].control_wz = u[r, 2].ctypes.data_as(fp)
             c_out[r].optimal_trajectory = traj[r].ctypes.data_as(fp)
-        rc = self._fn("optimize")(self._h, c_in, c_out)
+        if costmaps is None:
+            rc = self._fn("optimize")(self._h, c_in, c_out)
+        else:
+            maps = [costmaps] if isinstance(costmaps, tuple) else list(costmaps)
+            if len(maps) != self.R:
+                raise ValueError(f"expected {self.R} costmaps, got {len(maps)}")
+            keep = [np.ascontiguousarray(m[0], dtype=np.uint8) for m in maps]
+            views = (capi.MppiCostmapView * self.R)()
+            for r, (m, cells) in enumerate(zip(maps, keep)):
+                views[r].cells = cells.ctypes.data_as(C.POINTER(C.c_uint8))
+                views[r].size_x, views[r].size_y = cells.shape[1], cells.shape[0]
+                views[r].resolution, views[r].origin_x, views[r].origin_y = float(m[1]), float(m[2]), float(m[3])
+            rc = self._fn("optimize_in_place")(self._h, views, c_in, c_out)
         _raise_for(self._lib, self._h, rc)
         results = []
         for r in range(self.R):
@@ -285,8 +300,15 @@ class Optimizer(EngineBase):
     def setResidentCapture(self, enabled: bool) -> None:
         _raise_for(self._lib, self._h, self._lib.mppi_set_resident_capture(self._h, 1 if enabled else 0))
 
-    def timeE2E(self, cells: np.ndarray, resolution: float, origin, inputs, cycles: int) -> np.ndarray:
-        """Per-call seconds of `cycles` (upload costmap; optimize) pairs, timed inside the C library."""
+    def windowMissCount(self) -> int:
+        return int(self._lib.mppi_window_miss_count(self._h))
+
+    def h2dByteCount(self) -> int:
+        return int(self._lib.mppi_h2d_byte_count(self._h))
+
+    def timeE2E(self, cells: np.ndarray, resolution: float, origin, inputs, cycles: int, in_place: bool = False) -> np.ndarray:
+        """Per-call seconds of `cycles` control cycles timed inside the C library: (upload costmap; optimize)
+        pairs, or mppi_optimize_in_place calls."""
         ins = [inputs] if isinstance(inputs, CycleInput) else list(inputs)
         c_in = (capi.MppiCycleIn * self.R)(*[i.to_c() for i in ins])
         c_out = (capi.MppiCycleOut * self.R)()
@@ -294,7 +316,8 @@ class Optimizer(EngineBase):
         t = np.zeros(cycles, dtype=np.float64)
         rc = self._lib.mppi_time_e2e(
             self._h, cells.ctypes.data_as(C.POINTER(C.c_uint8)), cells.shape[1], cells.shape[0], float(resolution),
-            float(origin[0]), float(origin[1]), c_in, c_out, int(cycles), t.ctypes.data_as(C.POINTER(C.c_double)))
+            float(origin[0]), float(origin[1]), c_in, c_out, int(cycles), 1 if in_place else 0,
+            t.ctypes.data_as(C.POINTER(C.c_double)))
         _raise_for(self._lib, self._h, rc)
         return t
 

@@ -350,3 +350,73 @@ def test_fleet_matches_single_robot_handles():
     fleet.shutdown()
     for s_ in singles:
         s_.shutdown()
+
+
+def _lean_engine(env=None):
+    """A C1 handle (lean configuration -> single-launch cycles) with seeded injected noise; `env` is set only
+    while the handle is created (the library reads its switches in mppi_create)."""
+    import os
+    env = env or {}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        cfg = P.nav2_bringup_config()
+        opt = nb.Optimizer(cfg)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    nvx, nvy, nwz = S.seeded_noise(2000, 56, (cfg.vx_std, cfg.vy_std, cfg.wz_std), seed=5)
+    opt.setNoise(nvx, nvy, nwz)
+    return opt
+
+
+def test_in_place_costmap_matches_upload_then_optimize():
+    """mppi_optimize_in_place (costmap read where it lies, window-only upload) against mppi_upload_costmap +
+    mppi_optimize, bit for bit, over cycles with a moving robot and a changing costmap."""
+    two_call, in_place = _lean_engine(), _lean_engine()
+    pose = [10.0, 10.0, 0.0]
+    speed = (0.2, 0.0, 0.0)
+    for cycle in range(8):
+        cells = build_map("blocks", seed=30 + cycle // 3)        # the costmap changes every third cycle
+        path = S.arc_path(tuple(pose), n_points=100)
+        inp = nb.CycleInput(pose=tuple(pose), speed=speed, path=path, goal_checker_xy_tolerance=0.25)
+        two_call.setCostmap(cells, 0.05, 0.0, 0.0)
+        a = two_call.evalControl(inp)
+        b = in_place.evalControl(inp, costmaps=(cells, 0.05, 0.0, 0.0))
+        np.testing.assert_array_equal(a.control_sequence, b.control_sequence, err_msg=f"cycle {cycle}")
+        np.testing.assert_array_equal(a.optimal_trajectory, b.optimal_trajectory)
+        assert a.cmd == b.cmd and a.furthest_reached_path_point == b.furthest_reached_path_point
+        pose[0] += 0.05 * a.cmd[0] * np.cos(pose[2]); pose[1] += 0.05 * a.cmd[0] * np.sin(pose[2]); pose[2] += 0.05 * a.cmd[2]
+        speed = (a.cmd[0], 0.0, a.cmd[2])
+    assert in_place.windowMissCount() == 0
+    # the borrowed costmap is gone after the call: the two-call entry point needs its own upload again
+    with pytest.raises(Exception):
+        in_place.evalControl(inp)
+    two_call.shutdown(); in_place.shutdown()
+
+
+def test_window_miss_repeats_the_cycle_with_the_whole_map():
+    """A window too small for the trajectories (forced): the kernel reports the miss, commits nothing, the cycle
+    runs again with the whole map, and every result equals a handle with the regular window."""
+    regular = _lean_engine()
+    tiny = _lean_engine({"MPPI_B200_WINDOW_HALF": "3"})        # 3 cells = 0.15 m either side of the robot
+    cells = build_map("blocks", seed=33)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    inp = nb.CycleInput(pose=(10.0, 10.0, 0.0), speed=(0.3, 0.0, 0.0), path=path, goal_checker_xy_tolerance=0.25)
+    for cycle in range(4):
+        a = regular.evalControl(inp, costmaps=(cells, 0.05, 0.0, 0.0))
+        b = tiny.evalControl(inp, costmaps=(cells, 0.05, 0.0, 0.0))
+        np.testing.assert_array_equal(a.control_sequence, b.control_sequence, err_msg=f"cycle {cycle}")
+        assert a.cmd == b.cmd
+    assert regular.windowMissCount() == 0
+    misses = tiny.windowMissCount()
+    assert misses >= 3        # the first cycle starts from a zero control sequence and can stay inside 0.15 m
+    # same through the two-call entry point (staged map, window-only upload, miss, whole map)
+    tiny.setCostmap(cells, 0.05, 0.0, 0.0); regular.setCostmap(cells, 0.05, 0.0, 0.0)
+    a = regular.evalControl(inp); b = tiny.evalControl(inp)
+    np.testing.assert_array_equal(a.control_sequence, b.control_sequence)
+    assert tiny.windowMissCount() == misses + 1
+    regular.shutdown(); tiny.shutdown()
