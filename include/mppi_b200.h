@@ -385,6 +385,10 @@ int mppi_set_state(MppiHandle * h, uint32_t robot, const MppiOptimizerState * st
  * no H2D, no D2H, no host sync.  The control sequence is restored first so every call does
  * identical work. */
 int mppi_enqueue_resident(MppiHandle * h, void * cuda_stream);
+/* `steps` such replays on the handle's own stream, each bracketed by CUDA events, after `warmup` untimed
+ * ones; ms_per_step receives `steps` device times.  flush_bytes > 0 flushes L2 before every replay by
+ * overwriting a buffer of that size (bench.py "value": larger than the 126 MB L2); 0 = hot L2. */
+int mppi_time_resident(MppiHandle * h, int steps, int warmup, size_t flush_bytes, float * ms_per_step);
 /* The scoring pass alone (kernel A in score_tensors mode + kernel B) on the state / trajectory tensors the
  * last mppi_optimize materialised (materialize_tensors = 1), everything resident: the kernel the
  * reference's critics correspond to, for roofline measurement. */

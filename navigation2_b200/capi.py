@@ -215,6 +215,7 @@ SYMBOLS = {
     "mppi_get_state": (C.c_int, [_P, C.c_uint32, C.POINTER(MppiOptimizerState)]),
     "mppi_set_state": (C.c_int, [_P, C.c_uint32, C.POINTER(MppiOptimizerState)]),
     "mppi_enqueue_resident": (C.c_int, [_P, _P]),
+    "mppi_time_resident": (C.c_int, [_P, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_float)]),
     "mppi_enqueue_score_resident": (C.c_int, [_P, _P]),
     "mppi_set_resident_capture": (C.c_int, [_P, C.c_int]),
     "mppi_time_e2e": (C.c_int, [_P, _U8, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double,

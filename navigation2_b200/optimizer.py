@@ -324,6 +324,14 @@ class Optimizer(EngineBase):
     def enqueueResident(self, cuda_stream: int | None = None) -> None:
         _raise_for(self._lib, self._h, self._lib.mppi_enqueue_resident(self._h, cuda_stream))
 
+    def timeResident(self, steps: int, warmup: int = 3, flush_bytes: int = 0) -> np.ndarray:
+        """Device milliseconds of `steps` resident replays, CUDA events inside the library (no binding overhead
+        between the events); flush_bytes > 0 flushes L2 before every replay."""
+        ms = np.zeros(steps, dtype=np.float32)
+        rc = self._lib.mppi_time_resident(self._h, int(steps), int(warmup), int(flush_bytes), ms.ctypes.data_as(C.POINTER(C.c_float)))
+        _raise_for(self._lib, self._h, rc)
+        return ms.astype(np.float64)
+
     def enqueueScoreResident(self, cuda_stream: int | None = None) -> None:
         _raise_for(self._lib, self._h, self._lib.mppi_enqueue_score_resident(self._h, cuda_stream))
 
