@@ -20,6 +20,7 @@
 #define MPPI_FUSED_THREADS 512  // 4 roles x MPPI_FUSED_G
 #define MPPI_PHASE_CLOCK_WORDS (MPPI_FUSED_MAX_CLUSTER * (MPPI_FUSED_THREADS / 32) * 32)  // per robot
 #define MPPI_FUSED_MAX_CLUSTER 16
+#define MPPI_FINALIZE_MAX_SEGMENTS 6  // k_finalize: segments a column of block partials is summed in
 #define MPPI_MAX_WINDOW_HALF 96   // cells either side of the robot staged in shared memory
 #define MPPI_MAX_WINDOW_BYTES (((2 * MPPI_MAX_WINDOW_HALF + 1 + 15 + 15) & ~15) * (2 * MPPI_MAX_WINDOW_HALF + 1))
 
