@@ -385,7 +385,11 @@ std::tuple<geometry_msgs::msg::TwistStamped, std::vector<std::array<float, 3>>> 
   const geometry_msgs::msg::PoseStamped & robot_pose, const geometry_msgs::msg::Twist & robot_speed,
   const nav_msgs::msg::Path & plan, const geometry_msgs::msg::Pose & goal, nav2_core::GoalChecker * goal_checker)
 {
-  uploadCostmap();
+  // the caller holds the costmap mutex (controller.cpp:106-107): the costmap is read where it lies, like the
+  // critics read it during evalControl (cost_critic.cpp:138-144), instead of being copied first
+  const MppiCostmapView costmap_view{
+    costmap_->getCharMap(), costmap_->getSizeInCellsX(), costmap_->getSizeInCellsY(),
+    costmap_->getResolution(), costmap_->getOriginX(), costmap_->getOriginY()};
   const size_t n = plan.poses.size();
   std::vector<double> px(n), py(n), pyaw(n);
   for (size_t i = 0; i < n; ++i) {
@@ -418,8 +422,8 @@ std::tuple<geometry_msgs::msg::TwistStamped, std::vector<std::array<float, 3>>> 
   out.control_vy = control_sequence_.vy.data();
   out.control_wz = control_sequence_.wz.data();
   out.optimal_trajectory = traj.data();
-  const int rc = mppi_optimize(handle_, &in, &out);
-  if (rc != MPPI_OK) {throwStatus(rc, "mppi_optimize");}
+  const int rc = mppi_optimize_in_place(handle_, &costmap_view, &in, &out);
+  if (rc != MPPI_OK) {throwStatus(rc, "mppi_optimize_in_place");}
   if (out.status == MPPI_ERR_NO_VALID_CONTROL) {
     throw nav2_core::NoValidControl("Optimizer fail to compute path");  // optimizer.cpp:294
   }
