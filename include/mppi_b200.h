@@ -150,6 +150,12 @@ typedef struct MppiConfig
   int32_t visualize;               /* keep per-critic cost arrays + collision flags (critic_manager.cpp:79-120) */
   int32_t materialize_tensors;     /* write state.v*, state.cv*, trajectories.x/y/yaws to HBM every iteration so
                                       mppi_get_tensor can return what the plugin API exposes (CriticData refs) */
+  /* TrajectoryVisualizer "trajectory_step" / "time_step" (trajectory_visualizer.cpp:38-39, defaults 5 / 3): with
+   * `visualize` set, every trajectory_step-th candidate trajectory is kept at every time_step-th point
+   * (MPPI_TENSOR_VIS_XY) — exactly what TrajectoryVisualizer::add reads (:144,177) — without materialising the
+   * B x T tensors.  0 = keep no samples. */
+  uint32_t vis_trajectory_step;
+  uint32_t vis_time_step;
 
   /* --- TrajectoryValidator (optimal_trajectory_validator.hpp:87-103) --- */
   int32_t validator_enabled;       /* 0 = no validation (always SUCCESS) */
@@ -237,6 +243,8 @@ typedef enum MppiTensor
   MPPI_TENSOR_COST_CELLS = 15,      /* uint32[n_s * B]: CostCritic cell index per strided sample, 0xFFFFFFFF off-map, 0xFFFFFFFE not visited (debug_cells) */
   MPPI_TENSOR_OBSTACLE_CELLS = 16,  /* uint32[T * B]: ObstaclesCritic cell index per step, same sentinels (debug_cells) */
   MPPI_TENSOR_SOFTMAX = 17,         /* float[B]: unnormalised softmax weights exp(-(c - min)/temperature) */
+  MPPI_TENSOR_VIS_XY = 19,          /* float[ceil(B / vis_trajectory_step)][ceil(T / vis_time_step)][2]: x, y of the candidate
+                                       trajectories the visualizer draws (visualize + vis_trajectory_step > 0) */
   MPPI_TENSOR_PHASE_CLOCKS = 18     /* int64[16 * 16 * 32]: SM clock at the phase boundaries of the fused kernel, per cluster rank and warp
                                        (tracing; enabled by the environment variable MPPI_B200_PHASE_CLOCKS=1) */
 } MppiTensor;

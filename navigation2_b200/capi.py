@@ -53,6 +53,7 @@ TENSOR_COST_CELLS = 15
 TENSOR_OBSTACLE_CELLS = 16
 TENSOR_SOFTMAX = 17
 TENSOR_PHASE_CLOCKS = 18
+TENSOR_VIS_XY = 19
 
 
 class MppiCriticParams(C.Structure):
@@ -111,6 +112,8 @@ class MppiConfig(C.Structure):
         ("critics", MppiCriticParams * MPPI_MAX_CRITICS),
         ("visualize", C.c_int32),
         ("materialize_tensors", C.c_int32),
+        ("vis_trajectory_step", C.c_uint32),
+        ("vis_time_step", C.c_uint32),
         ("validator_enabled", C.c_int32),
         ("collision_lookahead_time", C.c_float),
         ("validator_consider_footprint", C.c_int32),

@@ -101,6 +101,8 @@ struct MppiHandle
   uint8_t * d_collisions = nullptr;
   uint32_t * d_dbg_cost = nullptr, * d_dbg_obs = nullptr;
   int32_t * d_red = nullptr;
+  float * d_vis_xy = nullptr;     // TrajectoryVisualizer samples [R][vis_n_traj][vis_n_pts][2]
+  int vis_n_traj = 0, vis_n_pts = 0;
   long long * d_phase_clocks = nullptr;
   bool defer_map_upload = false;  // the last cycle was single-launch: mppi_optimize moves map + cycle block in one copy
   bool single_copy = true;        // MPPI_B200_NO_SINGLE_COPY=1: side-stream map upload + copy node, as on the general path
@@ -176,7 +178,7 @@ void free_device(MppiHandle * h)
   F(h->d_u); F(h->d_u_saved); F(h->d_hist); F(h->d_hist_saved); F(h->d_terms); F(h->d_obs_raw);
   F(h->d_obs_rep); F(h->d_last); F(h->d_pa); F(h->d_costs); F(h->d_softmax); F(h->d_critic_costs);
   F(h->d_collisions); F(h->d_dbg_cost); F(h->d_dbg_obs); F(h->d_red); F(h->d_partials); F(h->d_slot);
-  F(h->d_phase_clocks); F(h->d_slot_all); F(h->d_static); F(h->d_cycle_saved);
+  F(h->d_vis_xy); F(h->d_phase_clocks); F(h->d_slot_all); F(h->d_static); F(h->d_cycle_saved);
   h->d_out = nullptr;  // alias of the mapped h_out
   // the arena (costmaps + cycle block) outlives a reconfiguration: mppi_destroy frees it
   if (h->h_out) {cudaFreeHost(h->h_out); h->h_out = nullptr;}
@@ -437,6 +439,14 @@ int allocate(MppiHandle * h)
   if (h->cfg.visualize && n_critics > 0) {
     CU_CHECK(h, cudaMalloc(&h->d_critic_costs, R * n_critics * B * sizeof(float)));
     CU_CHECK(h, cudaMemset(h->d_critic_costs, 0, R * n_critics * B * sizeof(float)));
+  }
+  h->vis_n_traj = 0; h->vis_n_pts = 0;
+  if (h->cfg.visualize && h->cfg.vis_trajectory_step > 0 && h->cfg.vis_time_step > 0) {
+    h->vis_n_traj = static_cast<int>((B + h->cfg.vis_trajectory_step - 1) / h->cfg.vis_trajectory_step);
+    h->vis_n_pts = static_cast<int>((T + h->cfg.vis_time_step - 1) / h->cfg.vis_time_step);
+    const size_t n = static_cast<size_t>(R) * h->vis_n_traj * h->vis_n_pts * 2;
+    CU_CHECK(h, cudaMalloc(&h->d_vis_xy, n * sizeof(float)));
+    CU_CHECK(h, cudaMemset(h->d_vis_xy, 0, n * sizeof(float)));
   }
   if (h->cfg.debug_cells) {
     if (h->cc_ns > 0) {
@@ -805,6 +815,9 @@ KArgs make_args(MppiHandle * h)
   a.ar2_slot = h->d_slot; a.ar2_all = h->d_slot_all;
   a.costmap = h->d_map; a.map_stride = h->map_stride;
   a.win_packets = h->d_packets; a.map_resident = 1;
+  a.vis_xy = h->d_vis_xy;
+  a.vis_traj_step = static_cast<int>(h->cfg.vis_trajectory_step); a.vis_time_step = static_cast<int>(h->cfg.vis_time_step);
+  a.vis_n_traj = h->vis_n_traj; a.vis_n_pts = h->vis_n_pts;
   a.path = reinterpret_cast<const float *>(h->d_cycle_block + sizeof(DevCycle) * h->R);
   a.path_valid = h->d_cycle_block + sizeof(DevCycle) * h->R + sizeof(float) * 4 * h->max_path * h->R;
   a.cyc = reinterpret_cast<DevCycle *>(h->d_cycle_block);
@@ -877,7 +890,10 @@ LaunchPlan make_plan(MppiHandle * h)
   // fused path: the whole batch of a robot fits one thread-block cluster and nothing asks for the
   // full-feature kernels (tensor materialisation, debug dumps, visualisation, clamp_raw, input delay)
   p.fused = false;
-  if (h->allow_fused && h->cfg.shard_world == 1 && !p.ka.full && h->B <= MPPI_FUSED_G * MPPI_FUSED_MAX_CLUSTER) {
+  // (`visualize` alone is fine: the fused kernel writes per-critic costs, collision flags and the visualizer's
+  // strided trajectory samples itself)
+  const bool fused_excluded = h->cfg.materialize_tensors || h->cfg.debug_cells || h->cfg.clamp_raw_controls || lag > 0;
+  if (h->allow_fused && h->cfg.shard_world == 1 && !fused_excluded && h->B <= MPPI_FUSED_G * MPPI_FUSED_MAX_CLUSTER) {
     int cs = 1;
     while (cs * MPPI_FUSED_G < h->B) {cs *= 2;}
     // The fused kernel trades throughput for latency (one 512-thread CTA per SM, serial phases): it is
@@ -1528,7 +1544,7 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
         // single-launch plans: the cycle block already went up with the map (upload_arena); a copy node inside the
         // graph costs ~11 us of latency (measured), a stream-ordered copy ahead of a kernel-only graph ~5 us
         int crc = single_copy ? MPPI_OK : upload_cycle_block(h, h->stream);
-        if (crc == MPPI_OK && h->cfg.visualize) {
+        if (crc == MPPI_OK && h->cfg.visualize && !plan.fused) {
           if (cudaMemsetAsync(h->d_collisions, 0, static_cast<size_t>(h->B) * h->R, h->stream) != cudaSuccess) {crc = MPPI_ERR_CUDA;}
           if (h->d_critic_costs &&
             cudaMemsetAsync(h->d_critic_costs, 0, sizeof(float) * h->cfg.n_critics * h->B * h->R, h->stream) != cudaSuccess)
@@ -1575,7 +1591,7 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
         CU_CHECK(h, cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, h->stream));
         first = false;
       }
-      if (h->cfg.visualize) {
+      if (h->cfg.visualize && !plan.fused) {
         CU_CHECK(h, cudaMemsetAsync(h->d_collisions, 0, static_cast<size_t>(h->B) * h->R, h->stream));
         if (h->d_critic_costs) {
           CU_CHECK(h, cudaMemsetAsync(h->d_critic_costs, 0, sizeof(float) * h->cfg.n_critics * h->B * h->R, h->stream));
@@ -1773,6 +1789,10 @@ int mppi_get_tensor(MppiHandle * h, uint32_t robot, int32_t which, void * dst, s
       src = h->d_dbg_cost + static_cast<size_t>(h->cc_ns) * B * robot; bytes = static_cast<size_t>(h->cc_ns) * B * 4; break;
     case MPPI_TENSOR_OBSTACLE_CELLS:
       rc = need(h->d_dbg_obs, "obstacle cells"); src = h->d_dbg_obs + slab * robot; bytes = slab * 4; break;
+    case MPPI_TENSOR_VIS_XY:
+      rc = need(h->d_vis_xy, "visualizer samples (visualize with vis_trajectory_step / vis_time_step > 0)");
+      bytes = static_cast<size_t>(h->vis_n_traj) * h->vis_n_pts * 2 * sizeof(float);
+      src = h->d_vis_xy + static_cast<size_t>(robot) * h->vis_n_traj * h->vis_n_pts * 2; break;
     case MPPI_TENSOR_PHASE_CLOCKS:
       rc = need(h->d_phase_clocks, "phase clocks (set MPPI_B200_PHASE_CLOCKS=1)");
       src = h->d_phase_clocks + static_cast<size_t>(robot) * MPPI_PHASE_CLOCK_WORDS;

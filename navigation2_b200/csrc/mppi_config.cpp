@@ -48,6 +48,8 @@ int mppi_default_config(MppiConfig * cfg)
   cfg->n_critics = 0;                         // src/critic_manager.cpp:40 (empty list)
   cfg->visualize = 0;                         // src/controller.cpp:40
   cfg->materialize_tensors = 0;
+  cfg->vis_trajectory_step = 5;               // src/trajectory_visualizer.cpp:38
+  cfg->vis_time_step = 3;                     // src/trajectory_visualizer.cpp:39
   cfg->validator_enabled = 1;                 // optimizer.cpp:56-58 default validator plugin
   cfg->collision_lookahead_time = 2.0f;       // optimal_trajectory_validator.hpp:87
   cfg->validator_consider_footprint = 0;      // :98

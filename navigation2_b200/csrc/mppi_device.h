@@ -189,6 +189,9 @@ struct KArgs
   // Single-launch cycles upload only the window of the costmap the trajectories can plausibly reach, packed
   // row by row (win_w x win_h bytes per robot, next to the cycle block: one copy).  map_resident = 0 then:
   // `costmap` is stale, a lookup outside the window raises DevOutHeader::map_miss instead of reading it.
+  // TrajectoryVisualizer samples (MPPI_TENSOR_VIS_XY): [R][vis_n_traj][vis_n_pts][2], or null
+  float * vis_xy;
+  int32_t vis_traj_step, vis_time_step, vis_n_traj, vis_n_pts;
   const uint8_t * win_packets;  // robot r's rows start at DevCycle::win_packet_off
   int32_t map_resident;
   const float * path;   // [R][4][max_path]: x, y, yaw, integrated distance

@@ -282,7 +282,16 @@ void Optimizer::getParams()  // optimizer.cpp:77-161
   s.open_loop = open_loop ? 1 : 0;
   s.regenerate_noises = regenerate ? 1 : 0;
   s.visualize = visualize ? 1 : 0;
-  s.materialize_tensors = visualize ? 1 : 0;  // the visualizer reads the generated trajectories
+  s.materialize_tensors = 0;  // the visualizer's strided samples come from MPPI_TENSOR_VIS_XY, not from B x T tensors
+  {
+    // TrajectoryVisualizer's own parameters (trajectory_visualizer.cpp:36-39) decide which samples the device keeps
+    auto getVisParam = parameters_handler_->getParamGetter(name_ + ".TrajectoryVisualizer");
+    int trajectory_step = 5, time_step = 3;
+    getVisParam(trajectory_step, "trajectory_step", 5);
+    getVisParam(time_step, "time_step", 3);
+    s.vis_trajectory_step = static_cast<uint32_t>(std::max(trajectory_step, 1));
+    s.vis_time_step = static_cast<uint32_t>(std::max(time_step, 1));
+  }
   getParam(motion_model_name, "motion_model", std::string("diff_drive"));
   setMotionModel(motion_model_name);
   s.motion_model = motion_model_->modelId();

@@ -262,6 +262,9 @@ class Optimizer(EngineBase):
             out = np.zeros(((T - 1) // step + 1, B), dtype=np.uint32)
         elif which == capi.TENSOR_OBSTACLE_CELLS:
             out = np.zeros((T, B), dtype=np.uint32)
+        elif which == capi.TENSOR_VIS_XY:
+            ts, tt = max(1, int(self.cfg.vis_trajectory_step)), max(1, int(self.cfg.vis_time_step))
+            out = np.zeros(((B + ts - 1) // ts, (T + tt - 1) // tt, 2), dtype=np.float32)
         else:
             out = np.zeros((T, B), dtype=np.float32)
         rc = self._fn("get_tensor")(self._h, robot, which, out.ctypes.data_as(C.c_void_p), out.nbytes)

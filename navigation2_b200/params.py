@@ -17,7 +17,7 @@ _CONTROLLER_FIELDS = {
     "model_delay_wz", "clamp_raw_controls", "temperature", "gamma", "vx_max", "vx_min", "vy_max",
     "wz_max", "ax_max", "ax_min", "ay_max", "ay_min", "az_max", "vx_std", "vy_std", "wz_std",
     "retry_attempt_limit", "open_loop", "sgf_order", "controller_frequency", "regenerate_noises",
-    "visualize", "noise_seed", "materialize_tensors", "debug_cells", "n_robots", "shard_rank",
+    "visualize", "noise_seed", "materialize_tensors", "vis_trajectory_step", "vis_time_step", "debug_cells", "n_robots", "shard_rank",
     "shard_world", "min_turning_r",
 }
 _MOTION_MODEL_NAMES = {  # "motion_model" parameter values (optimizer.cpp:150, motion_models.xml)

@@ -420,3 +420,46 @@ def test_window_miss_repeats_the_cycle_with_the_whole_map():
     np.testing.assert_array_equal(a.control_sequence, b.control_sequence)
     assert tiny.windowMissCount() == misses + 1
     regular.shutdown(); tiny.shutdown()
+
+
+def test_visualize_on_the_single_launch_path_matches_the_general_kernels():
+    """`visualize` (bring-up default, nav2_params.yaml:157): per-critic cost arrays (critic_manager.cpp:79-117),
+    collision flags and the strided trajectory samples TrajectoryVisualizer::add draws
+    (trajectory_visualizer.cpp:144,177).  The single-launch kernel writes them itself; the general kernels (forced
+    with materialize_tensors) are the cross-check, and both are compared with the oracle's tensors."""
+    base = dict(batch_size=2000, time_steps=56, visualize=1, vis_trajectory_step=5, vis_time_step=3)
+    cfg_fused = P.nav2_bringup_config(**base)
+    cfg_general = P.nav2_bringup_config(materialize_tensors=1, **base)
+    cells = build_map("blocks", seed=41)
+    cells[180:230, 204:208] = 254                            # a wall 0.2 m ahead: some candidates collide
+    nvx, nvy, nwz = S.seeded_noise(2000, 56, (cfg_fused.vx_std, cfg_fused.vy_std, cfg_fused.wz_std), seed=8)
+    from oracle.binding import OracleOptimizer
+    engines = [nb.Optimizer(cfg_fused), nb.Optimizer(cfg_general)]
+    cpu = OracleOptimizer(cfg_general)
+    for e in engines + [cpu]:
+        e.setCostmap(cells, 0.05, 0.0, 0.0)
+        e.setNoise(nvx, nvy, nwz)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    inp = nb.CycleInput(pose=(10.0, 10.0, 0.0), speed=(0.3, 0.0, 0.0), path=path, goal_checker_xy_tolerance=0.25)
+    for cycle in range(3):
+        res = [e.evalControl(inp) for e in engines]
+        ref = cpu.evalControl(inp)
+        # the two paths reduce the softmax sums in a different order: last-ulp differences in the update
+        np.testing.assert_allclose(res[0].control_sequence, res[1].control_sequence, rtol=0, atol=1e-6)
+        f, g = engines
+        for t in (capi.TENSOR_COSTS, capi.TENSOR_CRITIC_COSTS, capi.TENSOR_COLLISIONS, capi.TENSOR_VIS_XY):
+            np.testing.assert_array_equal(f.getTensor(t), g.getTensor(t), err_msg=f"tensor {t} cycle {cycle}")
+        vis = f.getTensor(capi.TENSOR_VIS_XY)
+        assert vis.shape == (400, 19, 2)
+        x, y = cpu.getTensor(capi.TENSOR_X), cpu.getTensor(capi.TENSOR_Y)        # (T, B)
+        np.testing.assert_array_equal(vis[:, :, 0], x[::3, ::5].T)
+        np.testing.assert_array_equal(vis[:, :, 1], y[::3, ::5].T)
+        coll = f.getTensor(capi.TENSOR_COLLISIONS)
+        np.testing.assert_array_equal(coll, cpu.getTensor(capi.TENSOR_COLLISIONS))
+        assert 0 < coll.sum() < 2000
+        np.testing.assert_allclose(f.getTensor(capi.TENSOR_CRITIC_COSTS), cpu.getTensor(capi.TENSOR_CRITIC_COSTS), rtol=1e-4, atol=1e-5)
+        for e in engines:
+            e.setState(cpu.getState()); e.setControlSequence(cpu.getOptimalControlSequence())
+    assert f.launchCount() < g.launchCount()                 # one launch per cycle against four
+    for e in engines + [cpu]:
+        e.shutdown()
