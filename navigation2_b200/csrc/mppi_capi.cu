@@ -92,6 +92,13 @@ struct MppiHandle
 
   // device buffers
   float * d_noise[3] = {nullptr, nullptr, nullptr};   // vx, vy, wz
+  // regenerate_noises: the tensors of the NEXT cycle are drawn on the side stream while the host is between cycles
+  // (the reference's noise thread, noise_generator.cpp:98-106); the two sets swap roles every cycle
+  float * d_noise_next[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t noise_event = nullptr;
+  bool noise_prefetched = false;
+  bool noise_prefetch = true;      // MPPI_B200_NO_NOISE_PREFETCH=1: draw at the start of the cycle on its own stream
+  uint32_t noise_flip = 0;
   float * d_cv[3] = {nullptr, nullptr, nullptr};
   float * d_state[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // vx vy wz x y yaw
   float * d_u = nullptr, * d_u_saved = nullptr;
@@ -173,6 +180,8 @@ void free_device(MppiHandle * h)
 {
   auto F = [](auto *& p) {if (p) {cudaFree(p); p = nullptr;}};
   for (auto & p : h->d_noise) {F(p);}
+  for (auto & p : h->d_noise_next) {F(p);}
+  h->noise_prefetched = false;
   for (auto & p : h->d_cv) {F(p);}
   for (auto & p : h->d_state) {F(p);}
   F(h->d_u); F(h->d_u_saved); F(h->d_hist); F(h->d_hist_saved); F(h->d_terms); F(h->d_obs_raw);
@@ -407,6 +416,11 @@ int allocate(MppiHandle * h)
   const int n_critics = static_cast<int>(h->cfg.n_critics);
   for (int i = 0; i < 3; ++i) {CU_CHECK(h, cudaMalloc(&h->d_noise[i], bt * sizeof(float)));}
   CU_CHECK(h, cudaMemset(h->d_noise[1], 0, bt * sizeof(float)));
+  if (h->cfg.regenerate_noises && h->noise_prefetch) {
+    for (int i = 0; i < 3; ++i) {CU_CHECK(h, cudaMalloc(&h->d_noise_next[i], bt * sizeof(float)));}
+    CU_CHECK(h, cudaMemset(h->d_noise_next[1], 0, bt * sizeof(float)));
+    if (!h->noise_event) {CU_CHECK(h, cudaEventCreateWithFlags(&h->noise_event, cudaEventDisableTiming));}
+  }
   if (mat || h->cfg.clamp_raw_controls) {
     for (int i = 0; i < 3; ++i) {
       CU_CHECK(h, cudaMalloc(&h->d_cv[i], bt * sizeof(float)));
@@ -460,6 +474,7 @@ int allocate(MppiHandle * h)
   }
   if (const char * e = std::getenv("MPPI_B200_NO_SINGLE_COPY"); e && e[0] == '1') {h->single_copy = false;}
   if (const char * e = std::getenv("MPPI_B200_NO_WINDOW_ONLY"); e && e[0] == '1') {h->window_only = false;}
+  if (const char * e = std::getenv("MPPI_B200_NO_NOISE_PREFETCH"); e && e[0] == '1') {h->noise_prefetch = false;}
   if (const char * e = std::getenv("MPPI_B200_WINDOW_HALF"); e && std::atoi(e) > 0) {h->window_half_override = std::atoi(e);}
   if (const char * e = std::getenv("MPPI_B200_PHASE_CLOCKS"); e && e[0] == '1') {
     CU_CHECK(h, cudaMalloc(&h->d_phase_clocks, R * MPPI_PHASE_CLOCK_WORDS * sizeof(long long)));
@@ -569,17 +584,20 @@ int ensure_cycle_block(MppiHandle * h, int need_path)
   return ensure_arena(h, h->map_stride, need_path);
 }
 
-int generate_noise(MppiHandle * h, int robot)
+// next = false: into the tensors the coming kernels read, on the handle's stream; next = true: into the other set,
+// on the side stream (prefetch for the following cycle)
+int generate_noise(MppiHandle * h, int robot, bool next = false)
 {
   // one robot at a time: pointers offset to that robot's slab, R = 1, robot index in the counter
   const size_t slab = static_cast<size_t>(h->B) * h->T;
   HostRobot & rb = h->robots[robot];
   // robot index and epoch are folded into the Philox key so each (robot, reset) draws a fresh tensor
   const uint64_t seed = h->cfg.noise_seed ^ (static_cast<uint64_t>(robot) * 0x9E3779B97F4A7C15ull);
+  float ** set = next ? h->d_noise_next : h->d_noise;
   CU_CHECK(h, mppi_launch_philox(
-      h->d_noise[0] + robot * slab, h->d_noise[1] + robot * slab, h->d_noise[2] + robot * slab,
+      set[0] + robot * slab, set[1] + robot * slab, set[2] + robot * slab,
       h->B, h->T, 1, static_cast<int>(h->cfg.shard_rank) * h->B, seed, rb.noise_epoch,
-      h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std, h->holo, h->stream));
+      h->cfg.vx_std, h->cfg.vy_std, h->cfg.wz_std, h->holo, next ? h->side : h->stream));
   rb.noise_epoch++;
   rb.noise_injected = false;
   h->launches++;
@@ -1006,7 +1024,7 @@ uint64_t plan_key(const MppiHandle * h, const LaunchPlan & p)
   mix(p.sm_a.total); mix(p.sm_a.path_cap); mix(p.sm_a.noise_stages); mix(p.sm_a.off_win); mix(p.sm_a.off_ring);
   mix(p.block_a); mix(p.block_b); mix(p.path_cap);
   mix(p.ka.block); mix(p.ka.holo); mix(p.ka.full); mix(p.ka.crit_types); mix(p.ka.cc_step); mix(p.ka.pa_step);
-  mix(h->cycle_block_bytes); mix(h->max_path); mix(h->map_stride); mix(h->cfg.visualize); mix(h->single_copy);
+  mix(h->cycle_block_bytes); mix(h->max_path); mix(h->map_stride); mix(h->cfg.visualize); mix(h->single_copy); mix(h->noise_flip);
   return k;
 }
 
@@ -1256,6 +1274,7 @@ int mppi_destroy(MppiHandle * h)
   for (auto & e : h->resident_events) {cudaEventDestroy(e);}
   if (h->d_flush) {cudaFree(h->d_flush);}
   cudaEventDestroy(h->map_event);
+  if (h->noise_event) {cudaEventDestroy(h->noise_event);}
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->side);
   delete h;
@@ -1453,14 +1472,27 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
   for (int r = 0; r < h->R; ++r) {max_n = std::max<int>(max_n, in[r].n_path);}
   int rc = ensure_cycle_block(h, max_n);
   if (rc != MPPI_OK) {return rc;}
+  bool prefetch_noise = false;
   if (h->cfg.regenerate_noises) {
-    // noise thread analogue (noise_generator.cpp:98-106): fresh noise for this cycle
-    for (int r = 0; r < h->R; ++r) {
-      if (!h->robots[r].noise_injected) {
-        rc = generate_noise(h, r);
-        if (rc != MPPI_OK) {return rc;}
+    // noise thread analogue (noise_generator.cpp:98-106): fresh noise for this cycle.  Normally it was drawn on
+    // the side stream after the previous cycle was launched and only has to be swapped in; injected noise
+    // (mppi_set_noise) lives in one set only, so a handle with any injected robot draws in line instead.
+    bool any_injected = false;
+    for (int r = 0; r < h->R; ++r) {any_injected = any_injected || h->robots[r].noise_injected;}
+    prefetch_noise = h->d_noise_next[0] != nullptr && !any_injected;
+    if (prefetch_noise && h->noise_prefetched) {
+      CU_CHECK(h, cudaStreamWaitEvent(h->stream, h->noise_event, 0));
+      for (int i = 0; i < 3; ++i) {std::swap(h->d_noise[i], h->d_noise_next[i]);}
+      h->noise_flip ^= 1u;
+    } else {
+      for (int r = 0; r < h->R; ++r) {
+        if (!h->robots[r].noise_injected) {
+          rc = generate_noise(h, r);
+          if (rc != MPPI_OK) {return rc;}
+        }
       }
     }
+    h->noise_prefetched = false;
   }
   using clk = std::chrono::steady_clock;
   auto tick = [&](int slot, clk::time_point & t0) {
@@ -1599,6 +1631,15 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
       }
       rc = enqueue_iterations(h, h->stream, plan);
       if (rc != MPPI_OK) {return rc;}
+    }
+    if (prefetch_noise && !h->noise_prefetched) {
+      // the other set was last read by the previous cycle, which has completed: draw the next cycle's noise into it
+      for (int r = 0; r < h->R; ++r) {
+        rc = generate_noise(h, r, true);
+        if (rc != MPPI_OK) {return rc;}
+      }
+      CU_CHECK(h, cudaEventRecord(h->noise_event, h->side));
+      h->noise_prefetched = true;
     }
     tick(3, tp);
     CU_CHECK(h, cudaStreamSynchronize(h->stream));

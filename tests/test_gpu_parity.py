@@ -463,3 +463,32 @@ def test_visualize_on_the_single_launch_path_matches_the_general_kernels():
     assert f.launchCount() < g.launchCount()                 # one launch per cycle against four
     for e in engines + [cpu]:
         e.shutdown()
+
+
+def test_regenerate_noises_prefetch_matches_inline_generation():
+    """regenerate_noises (bring-up default, nav2_params.yaml:159): the next cycle's Philox tensors are drawn on the
+    side stream into the second set while the host is between cycles (the reference's noise thread,
+    noise_generator.cpp:98-106).  Same tensors, same commands as drawing them at the start of each cycle."""
+    import os
+    cfg = P.nav2_bringup_config(regenerate_noises=1)
+    prefetching = nb.Optimizer(cfg)
+    os.environ["MPPI_B200_NO_NOISE_PREFETCH"] = "1"
+    try:
+        inline = nb.Optimizer(cfg)
+    finally:
+        os.environ.pop("MPPI_B200_NO_NOISE_PREFETCH")
+    cells = build_map("blocks", seed=12)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    inp = nb.CycleInput(pose=(10.0, 10.0, 0.0), speed=(0.2, 0.0, 0.0), path=path, goal_checker_xy_tolerance=0.25)
+    previous = None
+    for cycle in range(6):
+        a = prefetching.evalControl(inp, costmaps=(cells, 0.05, 0.0, 0.0))
+        b = inline.evalControl(inp, costmaps=(cells, 0.05, 0.0, 0.0))
+        na, nb_ = prefetching.getTensor(capi.TENSOR_NOISE_VX), inline.getTensor(capi.TENSOR_NOISE_VX)
+        np.testing.assert_array_equal(na, nb_, err_msg=f"noise of cycle {cycle}")
+        np.testing.assert_array_equal(a.control_sequence, b.control_sequence, err_msg=f"cycle {cycle}")
+        assert previous is None or not np.array_equal(previous, na)     # a fresh tensor every cycle
+        previous = na
+        if cycle == 3:
+            prefetching.reset(); inline.reset()                          # reset draws again on both
+    prefetching.shutdown(); inline.shutdown()
