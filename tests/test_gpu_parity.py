@@ -492,3 +492,38 @@ def test_regenerate_noises_prefetch_matches_inline_generation():
         if cycle == 3:
             prefetching.reset(); inline.reset()                          # reset draws again on both
     prefetching.shutdown(); inline.shutdown()
+
+
+def test_in_place_fleet_and_arena_growth():
+    """Three robots in one handle through mppi_optimize_in_place (one window packet per robot, one copy for all),
+    against the two-call sequence; then a larger costmap and a longer path arrive mid-run (the pinned / device
+    arenas are reallocated, staged maps carried over) and the results still agree."""
+    R = 3
+    cfg = P.nav2_bringup_config(n_robots=R, batch_size=1000)
+    a, b = nb.Optimizer(cfg), nb.Optimizer(cfg)
+    noises = [S.seeded_noise(1000, 56, (0.2, 0.2, 0.4), seed=300 + r) for r in range(R)]
+    for r in range(R):
+        a.setNoise(*noises[r], robot=r); b.setNoise(*noises[r], robot=r)
+
+    def cycle(size, n_points, seed):
+        maps, inputs = [], []
+        for r in range(R):
+            cells = build_map("blocks", seed=seed + r, size=size, pose=(5.0, 5.0))
+            maps.append((cells, 0.05, 0.0, 0.0))
+            path = S.arc_path((5.0, 5.0, 0.1 * r), n_points=n_points, curvature=0.05 * (r - 1))
+            inputs.append(nb.CycleInput(pose=(5.0, 5.0, 0.1 * r), speed=(0.1 * (r + 1), 0.0, 0.0), path=path,
+                                        goal_checker_xy_tolerance=0.25))
+            a.setCostmap(cells, 0.05, 0.0, 0.0, robot=r)
+        ra = a.evalControl(inputs)
+        rb = b.evalControl(inputs, costmaps=maps)
+        for r in range(R):
+            np.testing.assert_array_equal(ra[r].control_sequence, rb[r].control_sequence, err_msg=f"robot {r}")
+            assert ra[r].cmd == rb[r].cmd
+
+    for k in range(2):
+        cycle(200, 80, 40 + 10 * k)
+    cycle(260, 80, 70)        # bigger costmap: the arenas grow
+    cycle(260, 300, 80)       # longer path than the cycle block's capacity: they grow again
+    cycle(200, 80, 90)        # and smaller inputs again
+    assert a.windowMissCount() == 0 and b.windowMissCount() == 0
+    a.shutdown(); b.shutdown()
