@@ -450,6 +450,19 @@ int mppi_shard_rollout(MppiHandle * h);                         /* kernel A: rol
 int mppi_shard_score(MppiHandle * h);                           /* kernels B, C: path critics, local softmax partials; then all-gather ar2 */
 int mppi_shard_update(MppiHandle * h, int last_iteration);      /* kernel D: combine slots, filter, constraints */
 int mppi_shard_end(MppiHandle * h, MppiCycleOut * out);         /* D2H + host state machine */
+/* The same cycle with both exchanges done on the device over peer memory (NVLink) instead of by a host-launched
+ * collective: every rank owns a mailbox its peers write into directly.  Setup, once per handle: each rank exports its
+ * mailbox (mppi_shard_ipc_handle, a 64-byte CUDA IPC handle), the caller all-gathers the handles (torch.distributed)
+ * and gives every rank all of them, rank-major (mppi_shard_open_peers).  Then mppi_shard_cycle, called by all ranks
+ * with the same inputs, is a whole evalControl: the kernels and the exchange kernels of an iteration are enqueued
+ * back to back, nothing goes through the host in between.  A peer that does not show up within 2 s fails the cycle
+ * (MPPI_ERR_CUDA) instead of hanging it. */
+int mppi_shard_ipc_handle(MppiHandle * h, unsigned char * handle64);
+int mppi_shard_open_peers(MppiHandle * h, const unsigned char * handles /* [shard_world][64] */);
+int mppi_shard_cycle(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out);
+/* `cycles` back-to-back mppi_shard_cycle calls (every rank calls it with the same arguments), each timed with
+ * steady_clock on the calling thread: the end-to-end latency of a sharded cycle free of binding overhead. */
+int mppi_time_shard_cycles(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out, int cycles, double * per_call_seconds);
 
 #ifdef __cplusplus
 }

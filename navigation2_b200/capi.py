@@ -240,6 +240,10 @@ SYMBOLS = {
     "mppi_shard_score": (C.c_int, [_P]),
     "mppi_shard_update": (C.c_int, [_P, C.c_int]),
     "mppi_shard_end": (C.c_int, [_P, C.POINTER(MppiCycleOut)]),
+    "mppi_shard_ipc_handle": (C.c_int, [_P, C.POINTER(C.c_ubyte)]),
+    "mppi_shard_open_peers": (C.c_int, [_P, C.POINTER(C.c_ubyte)]),
+    "mppi_shard_cycle": (C.c_int, [_P, C.POINTER(MppiCycleIn), C.POINTER(MppiCycleOut)]),
+    "mppi_time_shard_cycles": (C.c_int, [_P, C.POINTER(MppiCycleIn), C.POINTER(MppiCycleOut), C.c_int, C.POINTER(C.c_double)]),
 }
 
 _LIB = None

@@ -132,6 +132,14 @@ struct MppiHandle
   size_t packets_capacity = 0;
   size_t packets_used = 0;
   int window_half_override = 0;   // MPPI_B200_WINDOW_HALF=<cells>: shrink the staged window (tests force window misses)
+  // batch sharding over peer memory (k_shard_exchange): this rank's mailbox, the peers' mailboxes opened with CUDA IPC
+  unsigned char * d_mailbox = nullptr;
+  size_t mailbox_bytes = 0, mailbox_words_base = 0, mailbox_slots_base = 0, mailbox_words_stride = 0, mailbox_slots_stride = 0;
+  std::vector<void *> peer_mailboxes;     // [world]; own entry = d_mailbox
+  unsigned char ** d_peers = nullptr;     // the same pointers on the device
+  int32_t * d_xerror = nullptr, * h_xerror = nullptr;
+  bool peers_open = false;
+  uint32_t xseq = 0;                      // exchanges performed (sequence number = xseq + 1, parity = xseq & 1)
   uint8_t * d_flush = nullptr;    // mppi_time_resident: the buffer overwritten to flush L2
   size_t flush_bytes = 0;
   std::vector<cudaEvent_t> resident_events;
@@ -1272,6 +1280,12 @@ int mppi_destroy(MppiHandle * h)
   for (auto & p : h->timing_events_c) {cudaEventDestroy(p.first); cudaEventDestroy(p.second);}
   for (auto & rb : h->robots) {if (rb.stage_event) {cudaEventDestroy(rb.stage_event);}}
   for (auto & e : h->resident_events) {cudaEventDestroy(e);}
+  for (size_t p = 0; p < h->peer_mailboxes.size(); ++p) {
+    if (h->peer_mailboxes[p] && h->peer_mailboxes[p] != h->d_mailbox) {cudaIpcCloseMemHandle(h->peer_mailboxes[p]);}
+  }
+  if (h->d_mailbox) {cudaFree(h->d_mailbox);}
+  if (h->d_peers) {cudaFree(h->d_peers);}
+  if (h->h_xerror) {cudaFreeHost(h->h_xerror);}
   if (h->d_flush) {cudaFree(h->d_flush);}
   cudaEventDestroy(h->map_event);
   if (h->noise_event) {cudaEventDestroy(h->noise_event);}
@@ -2094,6 +2108,86 @@ int mppi_shard_buffers(
   return MPPI_OK;
 }
 
+namespace
+{
+size_t align256(size_t v) {return (v + 255) & ~static_cast<size_t>(255);}
+
+int ensure_mailbox(MppiHandle * h)
+{
+  if (h->d_mailbox) {return MPPI_OK;}
+  const size_t world = h->cfg.shard_world;
+  h->mailbox_words_stride = align256(sizeof(int32_t) * RED_WORDS * h->R);
+  h->mailbox_slots_stride = align256(sizeof(float) * (2 + 3 * h->T) * h->R);
+  h->mailbox_words_base = align256(sizeof(uint32_t) * 2 * 2 * world);
+  h->mailbox_slots_base = h->mailbox_words_base + 2 * world * h->mailbox_words_stride;
+  h->mailbox_bytes = h->mailbox_slots_base + 2 * world * h->mailbox_slots_stride;
+  CU_CHECK(h, cudaMalloc(&h->d_mailbox, h->mailbox_bytes));
+  CU_CHECK(h, cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));
+  CU_CHECK(h, cudaMalloc(&h->d_peers, sizeof(unsigned char *) * world));
+  // the timeout flag lives in mapped pinned memory: the host reads it after the cycle without another copy
+  CU_CHECK(h, cudaHostAlloc(&h->h_xerror, sizeof(int32_t), cudaHostAllocMapped));
+  *h->h_xerror = 0;
+  CU_CHECK(h, cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->d_xerror), h->h_xerror, 0));
+  return MPPI_OK;
+}
+
+int enqueue_exchange(MppiHandle * h, int kind)
+{
+  if (h->cfg.shard_world == 1) {  // nothing to exchange: the gathered slots are this rank's slot
+    if (kind == 1) {
+      CU_CHECK(h, cudaMemcpyAsync(h->d_slot_all, h->d_slot, sizeof(float) * (2 + 3 * h->T) * h->R, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return MPPI_OK;
+  }
+  ShardExchangeArgs x{};
+  x.peers = h->d_peers;
+  x.world = static_cast<int32_t>(h->cfg.shard_world); x.rank = static_cast<int32_t>(h->cfg.shard_rank);
+  x.kind = kind;
+  x.parity = static_cast<int32_t>(h->xseq & 1u);
+  x.seq = h->xseq + 1u;
+  x.payload_base = kind == 0 ? h->mailbox_words_base : h->mailbox_slots_base;
+  x.payload_stride = kind == 0 ? h->mailbox_words_stride : h->mailbox_slots_stride;
+  x.n_words = kind == 0 ? RED_WORDS * h->R : (2 + 3 * h->T) * h->R;
+  x.src = reinterpret_cast<const uint32_t *>(kind == 0 ? static_cast<void *>(h->d_red) : static_cast<void *>(h->d_slot));
+  x.dst = reinterpret_cast<uint32_t *>(kind == 0 ? static_cast<void *>(h->d_red) : static_cast<void *>(h->d_slot_all));
+  x.error = h->d_xerror;
+  CU_CHECK(h, mppi_launch_shard_exchange(x, h->stream));
+  h->xseq++;
+  h->launches++;
+  return MPPI_OK;
+}
+}  // namespace
+
+int mppi_shard_ipc_handle(MppiHandle * h, unsigned char * handle64)
+{
+  if (check_handle(h) != MPPI_OK || !handle64) {return MPPI_ERR_INVALID_ARGUMENT;}
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  int rc = ensure_mailbox(h);
+  if (rc != MPPI_OK) {return rc;}
+  cudaIpcMemHandle_t ipc;
+  CU_CHECK(h, cudaIpcGetMemHandle(&ipc, h->d_mailbox));
+  std::memcpy(handle64, &ipc, sizeof(ipc));
+  return MPPI_OK;
+}
+
+int mppi_shard_open_peers(MppiHandle * h, const unsigned char * handles)
+{
+  if (check_handle(h) != MPPI_OK || !handles) {return MPPI_ERR_INVALID_ARGUMENT;}
+  int rc = ensure_mailbox(h);
+  if (rc != MPPI_OK) {return rc;}
+  const uint32_t world = h->cfg.shard_world, rank = h->cfg.shard_rank;
+  h->peer_mailboxes.assign(world, nullptr);
+  for (uint32_t p = 0; p < world; ++p) {
+    if (p == rank) {h->peer_mailboxes[p] = h->d_mailbox; continue;}
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, handles + 64 * static_cast<size_t>(p), sizeof(ipc));
+    CU_CHECK(h, cudaIpcOpenMemHandle(&h->peer_mailboxes[p], ipc, cudaIpcMemLazyEnablePeerAccess));
+  }
+  CU_CHECK(h, cudaMemcpy(h->d_peers, h->peer_mailboxes.data(), sizeof(void *) * world, cudaMemcpyHostToDevice));
+  h->peers_open = true;
+  return MPPI_OK;
+}
+
 int mppi_shard_begin(MppiHandle * h, const MppiCycleIn * in)
 {
   if (!h || !in) {return MPPI_ERR_INVALID_ARGUMENT;}
@@ -2140,6 +2234,49 @@ int mppi_shard_update(MppiHandle * h, int last_iteration)
   a.last_iteration = last_iteration ? 1 : 0;
   CU_CHECK(h, mppi_launch_finalize(a, h->holo, 2, h->stream));
   h->launches += 1;
+  return MPPI_OK;
+}
+
+// A whole sharded evalControl with the two exchanges done on the device over peer memory: every rank calls it with
+// the same inputs; nothing between the kernels of an iteration goes through the host.
+int mppi_shard_cycle(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
+{
+  if (!h || !in || !out) {return MPPI_ERR_INVALID_ARGUMENT;}
+  if (!h->peers_open && h->cfg.shard_world > 1) {h->error = "mppi_shard_cycle needs mppi_shard_open_peers first"; return MPPI_ERR_NOT_READY;}
+  int rc = mppi_shard_begin(h, in);
+  if (rc != MPPI_OK) {return rc;}
+  const int iters = static_cast<int>(h->cfg.iteration_count);
+  while (true) {
+    for (int it = 0; it < iters; ++it) {
+      rc = mppi_shard_rollout(h);
+      if (rc == MPPI_OK) {rc = enqueue_exchange(h, 0);}
+      if (rc == MPPI_OK) {rc = mppi_shard_score(h);}
+      if (rc == MPPI_OK) {rc = enqueue_exchange(h, 1);}
+      if (rc == MPPI_OK) {rc = mppi_shard_update(h, it == iters - 1 ? 1 : 0);}
+      if (rc != MPPI_OK) {return rc;}
+    }
+    rc = mppi_shard_end(h, out);
+    if (rc == 1) {continue;}  // fallback(): every rank saw the same flags and retries together
+    if (rc != MPPI_OK) {return rc;}
+    break;
+  }
+  if (h->h_xerror && *static_cast<volatile int32_t *>(h->h_xerror)) {
+    h->error = "a peer did not reach an exchange within 2 s";
+    return MPPI_ERR_CUDA;
+  }
+  return MPPI_OK;
+}
+
+// `cycles` back-to-back mppi_shard_cycle calls, each timed with steady_clock on the calling thread (all ranks call it)
+int mppi_time_shard_cycles(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out, int cycles, double * per_call_seconds)
+{
+  if (!h || !in || !out || !per_call_seconds || cycles < 1) {return MPPI_ERR_INVALID_ARGUMENT;}
+  for (int i = 0; i < cycles; ++i) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = mppi_shard_cycle(h, in, out);
+    if (rc != MPPI_OK) {return rc;}
+    per_call_seconds[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
   return MPPI_OK;
 }
 

@@ -77,4 +77,22 @@ cudaError_t mppi_launch_philox(
 cudaError_t mppi_launch_selftest_exact_math(
   const float * a, const float * b, int n, unsigned int * mismatches, unsigned int * flagged, cudaStream_t stream);
 
+// One exchange of a sharded iteration over peer memory (k_shard_exchange).  Mailbox layout, identical on every rank:
+// uint32 seq[2 kinds][2 parities][world], then per kind a payload area [2 parities][world][payload_stride bytes].
+struct ShardExchangeArgs
+{
+  unsigned char * const * peers;   // device array of `world` mailbox base pointers (peers' opened with CUDA IPC)
+  int32_t world, rank;
+  int32_t kind;                    // 0: reduction words (MAX-reduced into dst), 1: softmax slots (gathered into dst)
+  int32_t parity;
+  uint32_t seq;
+  size_t payload_base;             // byte offset of this kind's payload area
+  size_t payload_stride;           // bytes per rank slot
+  int32_t n_words;                 // 4-byte words in one payload
+  const uint32_t * src;            // this rank's payload (device)
+  uint32_t * dst;                  // n_words (kind 0) or world * n_words (kind 1) words
+  int32_t * error;                 // set to 1 when a peer did not show up within the timeout
+};
+cudaError_t mppi_launch_shard_exchange(const ShardExchangeArgs & x, cudaStream_t stream);
+
 #endif  // NAVIGATION2_B200_CSRC_MPPI_KERNELS_H_

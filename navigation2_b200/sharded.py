@@ -12,6 +12,7 @@ not depend on the number of ranks.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -40,9 +41,12 @@ class ShardedOptimizer(Optimizer):
         self._distributed = self.world > 1
         if self._distributed and (not dist.is_initialized() or dist.get_world_size(group) != self.world):
             raise RuntimeError("shard_world does not match the torch.distributed world size")
-        # launch on torch's current stream so NCCL collectives are ordered against our kernels
-        stream = torch.cuda.current_stream().cuda_stream
-        _raise_for(self._lib, self._h, self._lib.mppi_set_stream(self._h, stream))
+        # Kernels and torch.distributed collectives must be ordered on ONE stream.  The legacy default stream has
+        # handle 0, which mppi_set_stream reads as "the handle's own stream": kernels and collectives would then run
+        # unordered (ranks diverge).  So a dedicated torch stream is used unless the caller already made one current.
+        cur = torch.cuda.current_stream()
+        self._stream = cur if cur.cuda_stream != 0 else torch.cuda.Stream()
+        _raise_for(self._lib, self._h, self._lib.mppi_set_stream(self._h, self._stream.cuda_stream))
         ar1, slot, slot_all = C.c_void_p(), C.c_void_p(), C.c_void_p()
         n1, n2 = C.c_size_t(), C.c_size_t()
         _raise_for(self._lib, self._h, self._lib.mppi_shard_buffers(
@@ -50,6 +54,20 @@ class ShardedOptimizer(Optimizer):
         self._ar1 = torch.as_tensor(_DeviceBuffer(ar1.value, n1.value, "<i4"), device="cuda")
         self._slot = torch.as_tensor(_DeviceBuffer(slot.value, n2.value, "<f4"), device="cuda")
         self._slot_all = torch.as_tensor(_DeviceBuffer(slot_all.value, n2.value * self.world, "<f4"), device="cuda")
+        # Exchanges over peer memory (k_shard_exchange): every rank exports its mailbox as a CUDA IPC handle, the
+        # handles are all-gathered once, and from then on a cycle never goes through the host between its kernels.
+        # MPPI_B200_NCCL_EXCHANGE=1 keeps the torch.distributed collectives between the kernels (A/B measurements).
+        self._peer_exchange = not self._distributed   # one rank: mppi_shard_cycle has nothing to exchange
+        if self._distributed and os.environ.get("MPPI_B200_NCCL_EXCHANGE", "0") != "1" and dist.get_backend(group) == "nccl":
+            mine = (C.c_ubyte * 64)()
+            _raise_for(self._lib, self._h, self._lib.mppi_shard_ipc_handle(self._h, mine))
+            t = torch.tensor(list(mine), dtype=torch.uint8, device="cuda")
+            gathered = torch.empty(64 * self.world, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(gathered, t, group=group)
+            handles = (C.c_ubyte * (64 * self.world))(*gathered.cpu().tolist())
+            _raise_for(self._lib, self._h, self._lib.mppi_shard_open_peers(self._h, handles))
+            dist.barrier(group=group)      # every mailbox is open everywhere before the first exchange
+            self._peer_exchange = True
 
     def evalControl(self, inp: CycleInput, raise_on_failure: bool = True) -> CycleResult:
         lib, h = self._lib, self._h
@@ -63,30 +81,55 @@ class ShardedOptimizer(Optimizer):
         c_out[0].control_vy = u[1].ctypes.data_as(fp)
         c_out[0].control_wz = u[2].ctypes.data_as(fp)
         c_out[0].optimal_trajectory = traj.ctypes.data_as(fp)
-        _raise_for(lib, h, lib.mppi_shard_begin(h, c_in))
-        iters = int(self.cfg.iteration_count)
-        while True:
-            for it in range(iters):
-                _raise_for(lib, h, lib.mppi_shard_rollout(h))
-                if self._distributed:
-                    self._dist.all_reduce(self._ar1, op=self._dist.ReduceOp.MAX, group=self._group)
-                _raise_for(lib, h, lib.mppi_shard_score(h))
-                if self._distributed:
-                    self._dist.all_gather_into_tensor(self._slot_all, self._slot, group=self._group)
-                else:
-                    self._slot_all.copy_(self._slot)
-                _raise_for(lib, h, lib.mppi_shard_update(h, 1 if it == iters - 1 else 0))
-            rc = lib.mppi_shard_end(h, c_out)
-            if rc == 1:
-                continue  # fallback(): every rank saw the same flags and retries together
-            _raise_for(lib, h, rc)
-            break
-        o = c_out[0]
+        if self._peer_exchange:
+            _raise_for(lib, h, lib.mppi_shard_cycle(h, c_in, c_out))
+            return self._result(c_out[0], u, traj, raise_on_failure)
+        with self._torch.cuda.stream(self._stream):   # the collectives order against the stream the kernels run on
+            _raise_for(lib, h, lib.mppi_shard_begin(h, c_in))
+            iters = int(self.cfg.iteration_count)
+            while True:
+                for it in range(iters):
+                    _raise_for(lib, h, lib.mppi_shard_rollout(h))
+                    if self._distributed:
+                        self._dist.all_reduce(self._ar1, op=self._dist.ReduceOp.MAX, group=self._group)
+                    _raise_for(lib, h, lib.mppi_shard_score(h))
+                    if self._distributed:
+                        self._dist.all_gather_into_tensor(self._slot_all, self._slot, group=self._group)
+                    else:
+                        self._slot_all.copy_(self._slot)
+                    _raise_for(lib, h, lib.mppi_shard_update(h, 1 if it == iters - 1 else 0))
+                rc = lib.mppi_shard_end(h, c_out)
+                if rc == 1:
+                    continue  # fallback(): every rank saw the same flags and retries together
+                _raise_for(lib, h, rc)
+                break
+        return self._result(c_out[0], u, traj, raise_on_failure)
+
+    def timeCycles(self, inp: CycleInput, cycles: int) -> np.ndarray:
+        """Per-call seconds of `cycles` sharded cycles with the exchanges over peer memory, timed inside the library
+        (every rank calls it)."""
+        if not self._peer_exchange:
+            raise RuntimeError("timeCycles needs the peer-memory exchange (NCCL backend)")
+        c_in = (capi.MppiCycleIn * 1)(inp.to_c())
+        c_out = (capi.MppiCycleOut * 1)()
+        T = self.T
+        u = np.zeros((3, T), dtype=np.float32)
+        traj = np.zeros((3, T), dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        c_out[0].control_vx = u[0].ctypes.data_as(fp)
+        c_out[0].control_vy = u[1].ctypes.data_as(fp)
+        c_out[0].control_wz = u[2].ctypes.data_as(fp)
+        c_out[0].optimal_trajectory = traj.ctypes.data_as(fp)
+        t = np.zeros(cycles, dtype=np.float64)
+        _raise_for(self._lib, self._h, self._lib.mppi_time_shard_cycles(self._h, c_in, c_out, int(cycles), t.ctypes.data_as(C.POINTER(C.c_double))))
+        return t
+
+    def _result(self, o, u, traj, raise_on_failure):
         res = CycleResult(status=o.status, cmd=(o.cmd_vx, o.cmd_vy, o.cmd_wz), control_sequence=u,
                           optimal_trajectory=traj.T.copy(), fail_flag=bool(o.fail_flag), validation=o.validation,
                           retries=o.retries, furthest_reached_path_point=o.furthest_reached_path_point)
         if raise_on_failure and res.status != capi.MPPI_OK:
-            _raise_for(lib, h, res.status)
+            _raise_for(self._lib, self._h, res.status)
         return res
 
 
