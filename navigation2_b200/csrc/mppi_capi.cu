@@ -139,6 +139,7 @@ struct MppiHandle
   unsigned char ** d_peers = nullptr;     // the same pointers on the device
   int32_t * d_xerror = nullptr, * h_xerror = nullptr;
   bool peers_open = false;
+  int shard_iteration = 0;                // iterations launched since mppi_shard_begin
   uint32_t xseq = 0;                      // exchanges performed (sequence number = xseq + 1, parity = xseq & 1)
   uint8_t * d_flush = nullptr;    // mppi_time_resident: the buffer overwritten to flush L2
   size_t flush_bytes = 0;
@@ -838,7 +839,7 @@ KArgs make_args(MppiHandle * h)
   a.collisions = h->d_collisions;
   a.dbg_cost_cells = h->d_dbg_cost; a.dbg_obstacle_cells = h->d_dbg_obs;
   a.red = h->d_red; a.partials = h->d_partials;
-  a.ar2_slot = h->d_slot; a.ar2_all = h->d_slot_all;
+  a.ar2_slot = h->d_slot; a.ar2_all = h->cfg.shard_world == 1 ? h->d_slot : h->d_slot_all;
   a.costmap = h->d_map; a.map_stride = h->map_stride;
   a.win_packets = h->d_packets; a.map_resident = 1;
   a.vis_xy = h->d_vis_xy;
@@ -2133,12 +2134,7 @@ int ensure_mailbox(MppiHandle * h)
 
 int enqueue_exchange(MppiHandle * h, int kind)
 {
-  if (h->cfg.shard_world == 1) {  // nothing to exchange: the gathered slots are this rank's slot
-    if (kind == 1) {
-      CU_CHECK(h, cudaMemcpyAsync(h->d_slot_all, h->d_slot, sizeof(float) * (2 + 3 * h->T) * h->R, cudaMemcpyDeviceToDevice, h->stream));
-    }
-    return MPPI_OK;
-  }
+  if (h->cfg.shard_world == 1) {return MPPI_OK;}  // nothing to exchange (make_args: the gathered slots ARE this rank's slot)
   ShardExchangeArgs x{};
   x.peers = h->d_peers;
   x.world = static_cast<int32_t>(h->cfg.shard_world); x.rank = static_cast<int32_t>(h->cfg.shard_rank);
@@ -2201,7 +2197,7 @@ int mppi_shard_begin(MppiHandle * h, const MppiCycleIn * in)
   }
   rc = upload_cycle_block(h, h->stream);
   if (rc != MPPI_OK) {return rc;}
-  CU_CHECK(h, cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, h->stream));
+  h->shard_iteration = 0;  // the first iteration starts from zero costs (KArgs::zero_costs, no memset)
   return wait_map(h, h->stream);
 }
 
@@ -2220,6 +2216,7 @@ int mppi_shard_score(MppiHandle * h)
   if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
   const LaunchPlan plan = make_plan(h);
   KArgs a = make_args(h);
+  a.zero_costs = h->shard_iteration == 0 ? 1 : 0;
   CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, false, plan.block_b, h->stream));
   CU_CHECK(h, mppi_launch_softmax_partial(a, h->holo, h->stream));
   CU_CHECK(h, mppi_launch_finalize(a, h->holo, 1, h->stream));
@@ -2234,6 +2231,7 @@ int mppi_shard_update(MppiHandle * h, int last_iteration)
   a.last_iteration = last_iteration ? 1 : 0;
   CU_CHECK(h, mppi_launch_finalize(a, h->holo, 2, h->stream));
   h->launches += 1;
+  h->shard_iteration++;
   return MPPI_OK;
 }
 
@@ -2243,8 +2241,10 @@ int mppi_shard_cycle(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
 {
   if (!h || !in || !out) {return MPPI_ERR_INVALID_ARGUMENT;}
   if (!h->peers_open && h->cfg.shard_world > 1) {h->error = "mppi_shard_cycle needs mppi_shard_open_peers first"; return MPPI_ERR_NOT_READY;}
+  const auto ht0 = std::chrono::steady_clock::now();
   int rc = mppi_shard_begin(h, in);
   if (rc != MPPI_OK) {return rc;}
+  const auto ht1 = std::chrono::steady_clock::now();
   const int iters = static_cast<int>(h->cfg.iteration_count);
   while (true) {
     for (int it = 0; it < iters; ++it) {
@@ -2255,7 +2255,15 @@ int mppi_shard_cycle(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
       if (rc == MPPI_OK) {rc = mppi_shard_update(h, it == iters - 1 ? 1 : 0);}
       if (rc != MPPI_OK) {return rc;}
     }
+    const auto ht2 = std::chrono::steady_clock::now();
     rc = mppi_shard_end(h, out);
+    if (h->host_timers) {
+      const auto ht3 = std::chrono::steady_clock::now();
+      h->ht[1] += std::chrono::duration<double>(ht1 - ht0).count();
+      h->ht[3] += std::chrono::duration<double>(ht2 - ht1).count();
+      h->ht[4] += std::chrono::duration<double>(ht3 - ht2).count();
+      h->ht_n++;
+    }
     if (rc == 1) {continue;}  // fallback(): every rank saw the same flags and retries together
     if (rc != MPPI_OK) {return rc;}
     break;
