@@ -246,7 +246,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cpu": cpu_model(), "host_cores": os.cpu_count(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_model():
@@ -427,7 +427,7 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     opt.shutdown()
     if distributed:
         dist.destroy_process_group()
@@ -532,7 +532,7 @@ def run_c4(args, world, rank, local_rank):
     total_ms = float(ms.item())
     units = batch * int(cfg.time_steps) * int(cfg.iteration_count)
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": units * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -541,13 +541,33 @@ def run_c4(args, world, rank, local_rank):
                                       + ("done by a kernel over peer memory (NVLink, CUDA IPC mailboxes)" if peer else
                                          "by torch.distributed (NCCL) between the kernels"),
                        "l2": "inputs (470 MB of noise per GPU at N=1) larger than L2"},
-            "gpu_launches": int(opt.launchCount())}), flush=True)
+            "gpu_launches": int(opt.launchCount())})
     opt.shutdown()
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # Native libraries write to stdout too (NCCL announces its version there at initialisation); the driver wants
+    # exactly one JSON line on stdout.  Everything else is sent to stderr: fd 1 is pointed at fd 2 for the whole
+    # run, the result line goes to a duplicate of the original stdout.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     from navigation2_b200 import build
     build.build_all()
