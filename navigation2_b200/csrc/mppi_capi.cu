@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -144,6 +145,8 @@ struct MppiHandle
   uint8_t * d_flush = nullptr;    // mppi_time_resident: the buffer overwritten to flush L2
   size_t flush_bytes = 0;
   std::vector<cudaEvent_t> resident_events;
+  uint32_t cycle_seq = 0;         // attempts launched; stamped into the result header by the kernels
+  bool poll_results = true;       // MPPI_B200_NO_POLL=1: wait for the stream instead of polling the result stamp
   uint64_t h2d_bytes = 0;         // bytes of costmaps, cycle blocks and window packets copied host -> device so far
   uint64_t window_misses = 0;     // window-only attempts that had to be repeated with the whole map
   bool window_only = true;        // MPPI_B200_NO_WINDOW_ONLY=1: single-launch cycles upload the whole map (A/B measurements)
@@ -483,6 +486,7 @@ int allocate(MppiHandle * h)
   }
   if (const char * e = std::getenv("MPPI_B200_NO_SINGLE_COPY"); e && e[0] == '1') {h->single_copy = false;}
   if (const char * e = std::getenv("MPPI_B200_NO_WINDOW_ONLY"); e && e[0] == '1') {h->window_only = false;}
+  if (const char * e = std::getenv("MPPI_B200_NO_POLL"); e && e[0] == '1') {h->poll_results = false;}
   if (const char * e = std::getenv("MPPI_B200_NO_NOISE_PREFETCH"); e && e[0] == '1') {h->noise_prefetch = false;}
   if (const char * e = std::getenv("MPPI_B200_WINDOW_HALF"); e && std::atoi(e) > 0) {h->window_half_override = std::atoi(e);}
   if (const char * e = std::getenv("MPPI_B200_PHASE_CLOCKS"); e && e[0] == '1') {
@@ -1564,6 +1568,8 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
     // One attempt = H2D of the cycle block, the optimize() iterations, D2H of the result block.  The
     // common case (first attempt, own stream, no per-kernel timing) replays a captured CUDA graph:
     // one launch call instead of one per node.  Addresses are fixed; the plan signature keys the cache.
+    h->cycle_seq++;
+    for (int r = 0; r < h->R; ++r) {h->hcyc(r)->seq = h->cycle_seq;}
     const bool graphable = h->use_graphs && first && !h->resident_capture && !h->timing && h->stream == h->own_stream;
     const bool single_copy = graphable && plan.fused && h->single_copy;
     // window-only: ship the rows of the costmap the trajectories can plausibly reach instead of the map (the
@@ -1657,7 +1663,26 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
       h->noise_prefetched = true;
     }
     tick(3, tp);
-    CU_CHECK(h, cudaStreamSynchronize(h->stream));
+    // The kernels stamp DevOutHeader::seq (mapped pinned memory) behind a system-scope fence once a robot's results
+    // are complete: polling it returns a few microseconds before the stream would report the kernel retired.
+    // Stream order still protects everything that follows; a cycle that does not stamp within 20 ms (an error,
+    // or a very large batch) falls back to waiting for the stream.
+    bool stamped = false;
+    if (h->poll_results) {
+      const auto p0 = std::chrono::steady_clock::now();
+      for (unsigned spins = 0; !stamped; ++spins) {
+        stamped = true;
+        for (int r = 0; r < h->R && stamped; ++r) {
+          if (!h->hcyc(r)->run) {continue;}
+          const volatile DevOutHeader * hdr = reinterpret_cast<const volatile DevOutHeader *>(h->h_out + static_cast<size_t>(r) * h->out_stride);
+          stamped = hdr->seq == h->cycle_seq;
+        }
+        if (!stamped && (spins & 255u) == 255u &&
+          std::chrono::steady_clock::now() - p0 > std::chrono::milliseconds(20)) {break;}
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (!stamped) {CU_CHECK(h, cudaStreamSynchronize(h->stream));}
     tick(4, tp);
     if (window_only) {
       bool missed = false;

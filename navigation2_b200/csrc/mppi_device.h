@@ -123,7 +123,7 @@ struct alignas(16) DevCycle
   int32_t furthest_cached;                  // CriticData::furthest_reached_path_point, -1 = unset
   int32_t fail_flag;                        // CriticData::fail_flag (sticky until prepare())
   int32_t run;                              // 0: this robot is idle in this attempt (fleet retries, score_tensors)
-  int32_t pad1;
+  uint32_t seq;                             // stamped into DevOutHeader::seq by the last iteration: the host polls for it
 };
 
 // Written by the finalize kernel, copied D2H once per call.  Followed in memory by
@@ -138,7 +138,8 @@ struct DevOutHeader
   float softmax_sum;
   int32_t map_miss;   // a lookup fell outside the uploaded costmap window while the full map was not resident:
                       // nothing was committed (control sequence, filter history); the host uploads the map and reruns
-  int32_t pad[3];
+  uint32_t seq;       // DevCycle::seq of the cycle these results belong to, written LAST behind a system-scope fence
+  int32_t pad[2];
 };
 
 struct KArgs
