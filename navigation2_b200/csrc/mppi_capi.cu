@@ -846,6 +846,7 @@ KArgs make_args(MppiHandle * h)
   a.ar2_slot = h->d_slot; a.ar2_all = h->cfg.shard_world == 1 ? h->d_slot : h->d_slot_all;
   a.costmap = h->d_map; a.map_stride = h->map_stride;
   a.win_packets = h->d_packets; a.map_resident = 1;
+  a.stamp_results = 0;
   a.vis_xy = h->d_vis_xy;
   a.vis_traj_step = static_cast<int>(h->cfg.vis_trajectory_step); a.vis_time_step = static_cast<int>(h->cfg.vis_time_step);
   a.vis_n_traj = h->vis_n_traj; a.vis_n_pts = h->vis_n_pts;
@@ -961,6 +962,7 @@ int enqueue_iterations(
 {
   KArgs a = make_args(h);
   a.map_resident = window_only ? 0 : 1;
+  a.stamp_results = (h->poll_results && source == CycleSource::LIVE) ? 1 : 0;
   const KArgs live = a;
   const int iters = static_cast<int>(h->cfg.iteration_count);
   // the path arrays never change within a cycle: they are read from the source block by every iteration
@@ -1037,7 +1039,7 @@ uint64_t plan_key(const MppiHandle * h, const LaunchPlan & p)
   mix(p.sm_a.total); mix(p.sm_a.path_cap); mix(p.sm_a.noise_stages); mix(p.sm_a.off_win); mix(p.sm_a.off_ring);
   mix(p.block_a); mix(p.block_b); mix(p.path_cap);
   mix(p.ka.block); mix(p.ka.holo); mix(p.ka.full); mix(p.ka.crit_types); mix(p.ka.cc_step); mix(p.ka.pa_step);
-  mix(h->cycle_block_bytes); mix(h->max_path); mix(h->map_stride); mix(h->cfg.visualize); mix(h->single_copy); mix(h->noise_flip);
+  mix(h->cycle_block_bytes); mix(h->max_path); mix(h->map_stride); mix(h->cfg.visualize); mix(h->single_copy); mix(h->noise_flip); mix(h->poll_results);
   return k;
 }
 

@@ -195,6 +195,7 @@ struct KArgs
   int32_t vis_traj_step, vis_time_step, vis_n_traj, vis_n_pts;
   const uint8_t * win_packets;  // robot r's rows start at DevCycle::win_packet_off
   int32_t map_resident;
+  int32_t stamp_results;   // the host polls DevOutHeader::seq: publish it behind a system-scope fence (costs ~2 us in the kernel)
   const float * path;   // [R][4][max_path]: x, y, yaw, integrated distance
   const uint8_t * path_valid;  // [R][max_path]
   DevCycle * cyc;       // [R]
