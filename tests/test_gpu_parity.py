@@ -527,3 +527,37 @@ def test_in_place_fleet_and_arena_growth():
     cycle(200, 80, 90)        # and smaller inputs again
     assert a.windowMissCount() == 0 and b.windowMissCount() == 0
     a.shutdown(); b.shutdown()
+
+
+@pytest.mark.parametrize("pose", [(0.3, 0.3, 0.8), (9.9, 0.2, 3.0), (9.85, 9.75, -2.3), (-0.4, 5.0, 0.0), (5.0, 10.6, -1.57)])
+def test_window_upload_at_map_edges_and_odd_sizes(pose):
+    """The packed costmap window at the borders of a 203 x 197 map (row pitch padded to 208, window clipped, right edge
+    rounded past size_x) and with the robot just outside the map: single-launch path through both entry points
+    against the oracle."""
+    from oracle.binding import OracleOptimizer
+    cfg = P.nav2_bringup_config(batch_size=1024, time_steps=40)
+    rng = np.random.default_rng(17)
+    cells = (rng.random((197, 203)) < 0.02).astype(np.uint8) * 254
+    cells[rng.random((197, 203)) < 0.05] = 120
+    cx, cy_ = int(np.clip(pose[0] / 0.05, 0, 202)), int(np.clip(pose[1] / 0.05, 0, 196))
+    cells[max(0, cy_ - 6):cy_ + 7, max(0, cx - 6):cx + 7] = 0          # free around the robot
+    nvx, nvy, nwz = S.seeded_noise(1024, 40, (cfg.vx_std, cfg.vy_std, cfg.wz_std), seed=3)
+    gpu_a, gpu_b, cpu = nb.Optimizer(cfg), nb.Optimizer(cfg), OracleOptimizer(cfg)
+    for e in (gpu_a, gpu_b, cpu):
+        e.setNoise(nvx, nvy, nwz)
+    gpu_a.setCostmap(cells, 0.05, 0.0, 0.0); cpu.setCostmap(cells, 0.05, 0.0, 0.0)
+    path = S.arc_path(pose, n_points=60, curvature=0.3)
+    inp = nb.CycleInput(pose=pose, speed=(0.2, 0.0, 0.1), path=path, goal_checker_xy_tolerance=0.25)
+    for cycle in range(3):
+        a = gpu_a.evalControl(inp, raise_on_failure=False)
+        b = gpu_b.evalControl(inp, raise_on_failure=False, costmaps=(cells, 0.05, 0.0, 0.0))
+        c = cpu.evalControl(inp, raise_on_failure=False)
+        assert a.status == b.status == c.status and a.retries == b.retries == c.retries
+        np.testing.assert_array_equal(a.control_sequence, b.control_sequence)
+        if c.status == 0:
+            np.testing.assert_allclose(a.control_sequence, c.control_sequence, rtol=0, atol=1e-5, err_msg=f"cycle {cycle}")
+            np.testing.assert_allclose(np.array(a.cmd), np.array(c.cmd), rtol=0, atol=1e-5)
+        for e in (gpu_a, gpu_b):
+            e.setState(cpu.getState()); e.setControlSequence(cpu.getOptimalControlSequence())
+    for e in (gpu_a, gpu_b, cpu):
+        e.shutdown()
