@@ -45,7 +45,8 @@ struct HostRobot
                                        // validity is evaluated on the host from it, O(n_path) lookups
   bool noise_injected = false;
   uint32_t noise_epoch = 0;
-  cudaEvent_t stage_event = nullptr;   // completion of the last H2D copy out of this robot's staging slab
+  cudaEvent_t stage_event = nullptr;   // completion of a slab copy this robot led (upload_stale_maps)
+  int stage_owner = 0;                 // the robot whose stage_event covers the last copy out of THIS robot's slab
   bool stage_pending = false;
   bool device_stale = false;     // the host-side map is newer than the device copy
   size_t map_bytes = 0;          // pitch * size_y
@@ -1053,17 +1054,33 @@ int upload_cycle_block(MppiHandle * h, cudaStream_t stream)
 // pinned staging -> device on the side stream for every robot whose device copy is behind its staging slab
 int upload_stale_maps(MppiHandle * h)
 {
+  // neighbouring robots whose slabs are full (map_bytes == map_stride, the usual fleet of equal maps) go up with
+  // one copy: 512 robots staged by mppi_optimize_in_place are one 20 MB transfer, not 512 enqueues
   bool any = false;
-  for (int r = 0; r < h->R; ++r) {
-    HostRobot & rb = h->robots[r];
-    if (!rb.device_stale || !rb.map_valid) {continue;}
+  int r = 0;
+  while (r < h->R) {
+    HostRobot & first = h->robots[r];
+    if (!first.device_stale || !first.map_valid) {++r; continue;}
+    int r1 = r + 1;
+    size_t bytes = first.map_bytes;
+    if (first.map_bytes == h->map_stride) {
+      while (r1 < h->R && h->robots[r1].device_stale && h->robots[r1].map_valid && h->robots[r1].map_bytes == h->map_stride) {++r1;}
+      bytes = h->map_stride * static_cast<size_t>(r1 - r);
+    }
     CU_CHECK(h, cudaMemcpyAsync(
-        h->d_map + h->map_stride * r, h->h_map_stage + h->map_stride * r, rb.map_bytes, cudaMemcpyHostToDevice, h->side));
-    h->h2d_bytes += rb.map_bytes;
-    CU_CHECK(h, cudaEventRecord(rb.stage_event, h->side));
-    rb.stage_pending = true;
-    rb.device_stale = false;
+        h->d_map + h->map_stride * r, h->h_map_stage + h->map_stride * r, bytes, cudaMemcpyHostToDevice, h->side));
+    h->h2d_bytes += bytes;
+    // one event per copy, owned by the first robot of the group: a robot's staging slab may be overwritten again
+    // once the event of the copy that last read it has completed
+    if (!first.stage_event) {CU_CHECK(h, cudaEventCreateWithFlags(&first.stage_event, cudaEventDisableTiming));}
+    CU_CHECK(h, cudaEventRecord(first.stage_event, h->side));
+    for (int q = r; q < r1; ++q) {
+      h->robots[q].stage_pending = true;
+      h->robots[q].stage_owner = r;
+      h->robots[q].device_stale = false;
+    }
     any = true;
+    r = r1;
   }
   if (any) {
     CU_CHECK(h, cudaEventRecord(h->map_event, h->side));
@@ -1285,7 +1302,6 @@ int mppi_destroy(MppiHandle * h)
   if (h->h_arena) {cudaFreeHost(h->h_arena);}
   for (auto & p : h->timing_events) {cudaEventDestroy(p.first); cudaEventDestroy(p.second);}
   for (auto & p : h->timing_events_c) {cudaEventDestroy(p.first); cudaEventDestroy(p.second);}
-  for (auto & rb : h->robots) {if (rb.stage_event) {cudaEventDestroy(rb.stage_event);}}
   for (auto & e : h->resident_events) {cudaEventDestroy(e);}
   for (size_t p = 0; p < h->peer_mailboxes.size(); ++p) {
     if (h->peer_mailboxes[p] && h->peer_mailboxes[p] != h->d_mailbox) {cudaIpcCloseMemHandle(h->peer_mailboxes[p]);}
@@ -1294,6 +1310,7 @@ int mppi_destroy(MppiHandle * h)
   if (h->d_peers) {cudaFree(h->d_peers);}
   if (h->h_xerror) {cudaFreeHost(h->h_xerror);}
   if (h->d_flush) {cudaFree(h->d_flush);}
+  for (auto & rb : h->robots) {if (rb.stage_event) {cudaEventDestroy(rb.stage_event);}}
   cudaEventDestroy(h->map_event);
   if (h->noise_event) {cudaEventDestroy(h->noise_event);}
   cudaStreamDestroy(h->own_stream);
@@ -1379,10 +1396,9 @@ int stage_map(
   HostRobot & rb = h->robots[robot];
   // the previous async copy out of THIS robot's staging slab must have drained before it is overwritten
   if (rb.stage_pending) {
-    CU_CHECK(h, cudaEventSynchronize(rb.stage_event));
+    CU_CHECK(h, cudaEventSynchronize(h->robots[rb.stage_owner].stage_event));
     rb.stage_pending = false;
   }
-  if (!rb.stage_event) {CU_CHECK(h, cudaEventCreateWithFlags(&rb.stage_event, cudaEventDisableTiming));}
   uint8_t * stage = h->h_map_stage + h->map_stride * robot;
   if (pitch == size_x) {
     std::memcpy(stage, cells, need);
