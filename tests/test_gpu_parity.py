@@ -561,3 +561,28 @@ def test_window_upload_at_map_edges_and_odd_sizes(pose):
             e.setState(cpu.getState()); e.setControlSequence(cpu.getOptimalControlSequence())
     for e in (gpu_a, gpu_b, cpu):
         e.shutdown()
+
+
+def test_measurement_entry_points():
+    """mppi_time_resident (event-timed replays, hot and with a flushed L2), mppi_h2d_byte_count (what bench.py reports
+    as h2d_bytes_per_step) and the launch counter."""
+    cfg = P.nav2_bringup_config()
+    opt = _lean_engine()
+    cells = build_map("blocks", seed=2)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    inp = nb.CycleInput(pose=(10.0, 10.0, 0.0), speed=(0.2, 0.0, 0.0), path=path, goal_checker_xy_tolerance=0.25)
+    opt.evalControl(inp, costmaps=(cells, 0.05, 0.0, 0.0))
+    b0, l0 = opt.h2dByteCount(), opt.launchCount()
+    for _ in range(4):
+        opt.evalControl(inp, costmaps=(cells, 0.05, 0.0, 0.0))
+    per_cycle = (opt.h2dByteCount() - b0) / 4
+    assert 4000 < per_cycle < 40000          # cycle block + packed window, not the 160 KB map
+    assert opt.launchCount() - l0 == 4       # one kernel per cycle
+    opt.setCostmap(cells, 0.05, 0.0, 0.0)
+    opt.setResidentCapture(True)
+    opt.evalControl(inp)
+    hot = opt.timeResident(20, 3, 0)
+    cold = opt.timeResident(20, 3, 256 << 20)
+    assert hot.shape == (20,) and np.all(hot > 0.005) and np.all(hot < 5.0)
+    assert np.median(cold) > np.median(hot)
+    opt.shutdown()
