@@ -17,10 +17,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "navigation2_b200", "csrc")
 LIB = os.path.join(ROOT, "navigation2_b200", "libmppi_b200.so")
 
-SOURCES = ["mppi_kernels.cu", "mppi_capi.cu", "mppi_config.cpp"]
+SOURCES = ["mppi_kernels.cu", "mppi_capi.cu", "mppi_config.cpp", "costmap_inflation.cu"]
 HEADERS = [
     os.path.join(ROOT, "include", "mppi_b200.h"),
     os.path.join(ROOT, "include", "mppi_math.h"),
+    os.path.join(ROOT, "include", "costmap_inflation_b200.h"),
     os.path.join(CSRC, "mppi_device.h"),
     os.path.join(CSRC, "mppi_kernels.h"),
 ]

@@ -80,3 +80,27 @@ def test_product_does_not_reference_the_oracle():
                 text = open(os.path.join(d, f)).read()
                 assert "oracle.binding" not in text and "mppi_oracle" not in text and "liboracle" not in text, \
                     f"{f} references the oracle"
+
+
+def test_inflation_header_symbols_are_exported_and_bound():
+    from navigation2_b200 import inflation
+    text = open(os.path.join(ROOT, "include", "costmap_inflation_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(costmap_inflation_[a-z_0-9]+)\s*\(", text)))
+    lib = inflation.load_library()
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/costmap_inflation_b200.h but not exported"
+        assert n in inflation.SYMBOLS, f"{n} has no ctypes prototype in navigation2_b200/inflation.py"
+    assert sorted(inflation.SYMBOLS) == names
+    import ctypes as C
+    assert C.sizeof(inflation.CostmapInflationConfig) == 40
+
+
+def test_inflation_fails_loudly_without_a_gpu():
+    import torch
+    from navigation2_b200 import inflation
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        inflation.InflationLayer(0.05, 0.22, inflation_radius=0.7)
