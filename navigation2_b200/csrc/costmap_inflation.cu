@@ -13,7 +13,7 @@
 //   * distance -> cost goes through a table indexed by the SQUARED distance, built on the host from the reference's
 //     own chain  sqrtf -> d * 100 + 0.5f -> cost_lut_  (inflation_layer.cpp:266-269), so the kernel has no float math.
 // One CTA produces a 64 x 32 tile: stage (64 + 2R) x (32 + 2R) raw cells in shared memory, two vertical sweeps
-// (one thread per column and direction), then one horizontal search per output cell.  Tiles whose staged region
+// (one thread per column), then one horizontal search per output cell (two cells per thread, packed add-then-min).  Tiles whose staged region
 // holds no seed (most of a sparse map) stop after the load and write nothing.
 //
 // In place is safe without a second buffer: a cell is written only by the CTA that owns it, after that CTA read it,
@@ -38,7 +38,8 @@ constexpr int TILE_W = 64;
 constexpr int TILE_H = 32;
 constexpr int THREADS = 256;
 constexpr int ROWS_PER_PASS = THREADS / TILE_W;  // 4
-constexpr unsigned FAR_SQ = 60000u;              // "no seed within R" in the uint16 squared-distance rows (R^2 <= 14400)
+static_assert(COSTMAP_INFLATION_MAX_CELL_RADIUS * COSTMAP_INFLATION_MAX_CELL_RADIUS < 40000, "squared radius must stay below FAR_SQ");
+constexpr unsigned FAR_SQ = 40000u;              // "no seed within R" in the uint16 squared distances: R^2 <= 14400 < FAR_SQ, FAR_SQ + R^2 < 65536
 constexpr int LUT_PRECISION = 100;               // InflationLayer::COST_LUT_PRECISION, inflation_layer.hpp:231
 constexpr uint8_t NO_INFORMATION = 255, LETHAL_OBSTACLE = 254, INSCRIBED_INFLATED_OBSTACLE = 253, FREE_SPACE = 0;
 
@@ -51,123 +52,189 @@ struct InflateArgs
   int min_i, min_j, max_i, max_j;  // clamped update window
   int radius;
   int inflate_unknown, inflate_around_unknown;
+  int aligned_rows;  // master, map_stride and size_x are multiples of 4: rows can be read as 32-bit words
 };
 
 struct SmemPlan
 {
   int raw_pitch, raw_rows, g_pitch;
-  size_t off_raw, off_down, off_up, off_sq, off_lut, total;
+  size_t off_raw, off_up, off_sq, off_dx, off_lut, total;
 };
 
 SmemPlan plan_smem(int radius)
 {
   SmemPlan p;
-  p.raw_pitch = (TILE_W + 2 * radius + 3) & ~3;
+  p.raw_pitch = (TILE_W + 2 * radius + 3 + 3) & ~3;  // + up to 3 bytes of alignment shift
   p.raw_rows = TILE_H + 2 * radius;
   p.g_pitch = p.raw_pitch;
   size_t o = 0;
   p.off_raw = o; o += static_cast<size_t>(p.raw_pitch) * p.raw_rows;
-  p.off_down = o; o += static_cast<size_t>(p.g_pitch) * TILE_H;
   p.off_up = o; o += static_cast<size_t>(p.g_pitch) * TILE_H;
   o = (o + 15) & ~static_cast<size_t>(15);
-  p.off_sq = o; o += static_cast<size_t>(p.g_pitch) * TILE_H * sizeof(uint16_t);
+  p.off_sq = o; o += static_cast<size_t>(p.g_pitch) * (TILE_H / 2) * sizeof(uint32_t);
+  p.off_dx = o; o += static_cast<size_t>(2 * radius + 1) * sizeof(uint32_t);
   p.off_lut = o; o += static_cast<size_t>(radius) * radius + 1;
   p.total = (o + 15) & ~static_cast<size_t>(15);
   return p;
 }
 
+// CR > 0: the cell radius is known at compile time (loops unroll, dx^2 become immediates); CR == 0: a.radius
+template<int CR>
 __global__ void __launch_bounds__(THREADS) k_inflate(const InflateArgs a, const SmemPlan sp)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ int s_row_has_seed[TILE_H];
+  __shared__ int s_row_has_seed[TILE_H / 2];
   uint8_t * s_raw = smem + sp.off_raw;
-  uint8_t * s_down = smem + sp.off_down;
   uint8_t * s_up = smem + sp.off_up;
-  uint16_t * s_sq = reinterpret_cast<uint16_t *>(smem + sp.off_sq);
+  uint32_t * s_sq = reinterpret_cast<uint32_t *>(smem + sp.off_sq);
+  uint32_t * s_dx = reinterpret_cast<uint32_t *>(smem + sp.off_dx);
   uint8_t * s_lut = smem + sp.off_lut;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int R = a.radius;
+  const int R = CR > 0 ? CR : a.radius;
   const int x0 = a.min_i + blockIdx.x * TILE_W, y0 = a.min_j + blockIdx.y * TILE_H;
   uint8_t * master = a.master + static_cast<size_t>(blockIdx.z) * a.map_stride;
   const int region_w = TILE_W + 2 * R, region_h = TILE_H + 2 * R;
   const bool around_unknown = a.inflate_around_unknown != 0;
+  const unsigned seed_span = around_unknown ? 1u : 0u;  // seed <=> cell - 254 <= span (254, or 254 and 255)
 
   // ---- stage the tile and its halo (cells outside the map hold no seed) ----
-  int seen_seed = 0;
-  for (int ry = warp; ry < region_h; ry += THREADS / 32) {
-    const int gy = y0 - R + ry;
-    const bool row_in = gy >= 0 && gy < a.size_y;
-    const uint8_t * src = master + static_cast<size_t>(row_in ? gy : 0) * a.size_x;
-    for (int rx = lane; rx < region_w; rx += 32) {
-      const int gx = x0 - R + rx;
-      uint8_t c = FREE_SPACE;
-      if (row_in && gx >= 0 && gx < a.size_x) {c = __ldg(src + gx);}
-      s_raw[ry * sp.raw_pitch + rx] = c;
-      seen_seed |= (c == LETHAL_OBSTACLE) | (around_unknown & (c == NO_INFORMATION));
+  // With 4-byte aligned rows the region is fetched as 32-bit words starting at the aligned column `xa`; the
+  // staged rows then begin `shift` bytes before the region's first column.
+  const bool words = a.aligned_rows != 0;
+  const int xa = words ? ((x0 - R) & ~3) : (x0 - R);
+  const int shift = (x0 - R) - xa;
+  unsigned seen_seed = 0;
+  if (words) {
+    const int n_words = (region_w + shift + 3) >> 2;
+    const unsigned unknown_word = around_unknown ? 0xFFFFFFFFu : 0xFEFEFEFEu;
+    for (int w = lane; w < n_words; w += 32) {
+      const int gx = xa + 4 * w;  // size_x is a multiple of 4: a word is inside the row or outside it
+      const bool col_in = gx >= 0 && gx < a.size_x;
+      int gy = y0 - R + warp;
+      const uint8_t * src = master + static_cast<ptrdiff_t>(gy) * a.size_x + gx;
+      uint32_t * dst = reinterpret_cast<uint32_t *>(s_raw + warp * sp.raw_pitch) + w;
+      const size_t src_step = static_cast<size_t>(THREADS / 32) * a.size_x;
+      const int dst_step = (THREADS / 32) * (sp.raw_pitch >> 2);
+#pragma unroll 4
+      for (int ry = warp; ry < region_h; ry += THREADS / 32) {
+        uint32_t cells = 0u;
+        if (col_in && static_cast<unsigned>(gy) < static_cast<unsigned>(a.size_y)) {
+          cells = __ldg(reinterpret_cast<const uint32_t *>(src));
+        }
+        *dst = cells;
+        seen_seed |= __vcmpeq4(cells, 0xFEFEFEFEu) | __vcmpeq4(cells, unknown_word);
+        gy += THREADS / 32; src += src_step; dst += dst_step;
+      }
+    }
+  } else {
+    for (int ry = warp; ry < region_h; ry += THREADS / 32) {
+      const int gy = y0 - R + ry;
+      const bool row_in = gy >= 0 && gy < a.size_y;
+      const uint8_t * src = master + static_cast<size_t>(row_in ? gy : 0) * a.size_x;
+      for (int rx = lane; rx < region_w; rx += 32) {
+        const int gx = x0 - R + rx;
+        uint8_t c = FREE_SPACE;
+        if (row_in && gx >= 0 && gx < a.size_x) {c = __ldg(src + gx);}
+        s_raw[ry * sp.raw_pitch + rx] = c;
+        seen_seed |= (static_cast<unsigned>(c) - 254u <= seed_span) ? 1u : 0u;
+      }
     }
   }
-  if (tid < TILE_H) {s_row_has_seed[tid] = 0;}
-  if (!__syncthreads_or(seen_seed)) {return;}  // nothing within R of this tile: every cell is skipped (:259-261)
+  if (tid < TILE_H / 2) {s_row_has_seed[tid] = 0;}
+  if (!__syncthreads_or(seen_seed != 0u)) {return;}  // nothing within R of this tile: every cell is skipped (:259-261)
   for (int i = tid; i <= R * R; i += THREADS) {s_lut[i] = __ldg(a.cost_by_sq + i);}
-
-  // ---- vertical sweeps: distance to the nearest seed above (down sweep) and below (up sweep), capped at 255 ----
-  for (int job = tid; job < 2 * region_w; job += THREADS) {
-    const bool upward = job >= region_w;
-    const int col = upward ? job - region_w : job;
-    uint8_t * dst = upward ? s_up : s_down;
-    unsigned dist = 255u;
-    for (int step = 0; step < region_h; ++step) {
-      const int y = upward ? region_h - 1 - step : step;
-      const uint8_t c = s_raw[y * sp.raw_pitch + col];
-      const bool seed = (c == LETHAL_OBSTACLE) | (around_unknown & (c == NO_INFORMATION));
-      dist = seed ? 0u : min(dist + 1u, 255u);
-      const int out_row = y - R;
-      if (out_row >= 0 && out_row < TILE_H) {dst[out_row * sp.g_pitch + col] = static_cast<uint8_t>(dist);}
+  if (CR == 0) {
+    for (int i = tid; i <= 2 * R; i += THREADS) {
+      const unsigned dx_sq = static_cast<unsigned>((i - R) * (i - R));
+      s_dx[i] = dx_sq | (dx_sq << 16);
     }
   }
-  __syncthreads();
 
-  // ---- squared column distances (FAR_SQ beyond R) and which tile rows can reach a seed at all ----
-  for (int r = warp; r < TILE_H; r += THREADS / 32) {
-    int any = 0;
-    for (int col = lane; col < region_w; col += 32) {
-      const unsigned g = min(static_cast<unsigned>(s_down[r * sp.g_pitch + col]), static_cast<unsigned>(s_up[r * sp.g_pitch + col]));
+  // ---- vertical pass, one thread per column: distance to the nearest seed below (up sweep over the halo below
+  //      the tile, then the tile rows), then to the nearest seed above (down sweep), combined into squared column
+  //      distances (FAR_SQ beyond R); tile rows r and r + 16 share one 32-bit word ----
+  uint16_t * s_sq16 = reinterpret_cast<uint16_t *>(s_sq);
+  const unsigned far_start = 2u * COSTMAP_INFLATION_MAX_CELL_RADIUS + TILE_H + 8u;  // larger than any reachable distance
+  for (int col = tid; col < region_w; col += THREADS) {
+    const uint8_t * cell = s_raw + (region_h - 1) * sp.raw_pitch + col + shift;
+    unsigned dist = far_start;
+    for (int i = 0; i < R; ++i) {  // halo below the tile
+      dist = (static_cast<unsigned>(*cell) - 254u <= seed_span) ? 0u : dist + 1u;
+      cell -= sp.raw_pitch;
+    }
+    uint8_t * up = s_up + (TILE_H - 1) * sp.g_pitch + col;
+#pragma unroll 4
+    for (int i = 0; i < TILE_H; ++i) {
+      dist = (static_cast<unsigned>(*cell) - 254u <= seed_span) ? 0u : dist + 1u;
+      *up = static_cast<uint8_t>(min(dist, 255u));
+      cell -= sp.raw_pitch;
+      up -= sp.g_pitch;
+    }
+    cell = s_raw + col + shift;
+    dist = far_start;
+    for (int i = 0; i < R; ++i) {  // halo above the tile
+      dist = (static_cast<unsigned>(*cell) - 254u <= seed_span) ? 0u : dist + 1u;
+      cell += sp.raw_pitch;
+    }
+    up = s_up + col;
+#pragma unroll 4
+    for (int r = 0; r < TILE_H; ++r) {
+      dist = (static_cast<unsigned>(*cell) - 254u <= seed_span) ? 0u : dist + 1u;
+      const unsigned g = min(dist, static_cast<unsigned>(*up));
       const bool near = g <= static_cast<unsigned>(R);
-      s_sq[r * sp.g_pitch + col] = static_cast<uint16_t>(near ? g * g : FAR_SQ);
-      any |= near ? 1 : 0;
+      s_sq16[(((r & (TILE_H / 2 - 1)) * sp.g_pitch + col) << 1) + (r >> 4)] = static_cast<uint16_t>(near ? g * g : FAR_SQ);
+      if (near) {s_row_has_seed[r & (TILE_H / 2 - 1)] = 1;}
+      cell += sp.raw_pitch;
+      up += sp.g_pitch;
     }
-    any = __any_sync(0xffffffffu, any);
-    if (lane == 0) {s_row_has_seed[r] = any;}
   }
   __syncthreads();
 
-  // ---- horizontal search, cost lookup and the merge rule of applyInflation (:263-276) ----
+  // ---- horizontal search (one add-then-min instruction per tap for two cells), cost lookup and the merge rule
+  //      of applyInflation (:263-276) ----
   const int c = tid & (TILE_W - 1);
   const int gx = x0 + c;
   const unsigned r_sq = static_cast<unsigned>(R * R);
   const bool inflate_unknown = a.inflate_unknown != 0;
-  for (int r = tid / TILE_W; r < TILE_H; r += ROWS_PER_PASS) {
-    const int gy = y0 + r;
-    if (!s_row_has_seed[r] || gx >= a.max_i || gy >= a.max_j) {continue;}
-    const uint16_t * row = s_sq + r * sp.g_pitch + c;  // row[k] is column gx - R + k
-    unsigned best = FAR_SQ;
-    unsigned dx_sq = r_sq;
-    int delta = -(2 * R - 1);  // (dx + 1)^2 - dx^2 at dx = -R
+  if (gx >= a.max_i) {return;}
+  for (int r = tid / TILE_W; r < TILE_H / 2; r += ROWS_PER_PASS) {
+    if (!s_row_has_seed[r]) {continue;}
+    const uint32_t * row = s_sq + r * sp.g_pitch + c;  // row[k] is column gx - R + k
+    unsigned best = FAR_SQ | (FAR_SQ << 16);
+    if (CR > 0) {
+#pragma unroll
+      for (int k = 0; k <= 2 * CR; ++k) {
+        const unsigned dx_sq = static_cast<unsigned>((k - CR) * (k - CR));
+        best = __viaddmin_u16x2(row[k], dx_sq | (dx_sq << 16), best);  // per half: min(column distance^2 + dx^2, best)
+      }
+    } else {
 #pragma unroll 4
-    for (int k = 0; k <= 2 * R; ++k) {
-      best = min(best, static_cast<unsigned>(row[k]) + dx_sq);
-      dx_sq += delta;
-      delta += 2;
+      for (int k = 0; k <= 2 * R; ++k) {
+        best = __viaddmin_u16x2(row[k], s_dx[k], best);
+      }
     }
-    if (best > r_sq) {continue;}
-    const uint8_t cost = s_lut[best];
-    const uint8_t before = s_raw[(r + R) * sp.raw_pitch + c + R];
-    const bool fill_unknown = before == NO_INFORMATION &&
-      (inflate_unknown ? cost > FREE_SPACE : cost >= INSCRIBED_INFLATED_OBSTACLE);
-    const uint8_t after = fill_unknown ? cost : max(before, cost);
-    if (after != before) {master[static_cast<size_t>(gy) * a.size_x + gx] = after;}
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const unsigned sq = half ? best >> 16 : best & 0xffffu;
+      const int tr = r + half * (TILE_H / 2);
+      const int gy = y0 + tr;
+      if (sq > r_sq || gy >= a.max_j) {continue;}
+      const uint8_t cost = s_lut[sq];
+      const uint8_t before = s_raw[(tr + R) * sp.raw_pitch + c + R + shift];
+      const bool fill_unknown = before == NO_INFORMATION &&
+        (inflate_unknown ? cost > FREE_SPACE : cost >= INSCRIBED_INFLATED_OBSTACLE);
+      const uint8_t after = fill_unknown ? cost : max(before, cost);
+      if (after != before) {master[static_cast<size_t>(gy) * a.size_x + gx] = after;}
+    }
   }
+}
+
+template<int CR>
+cudaError_t launch_inflate(dim3 grid, size_t smem, cudaStream_t stream, const InflateArgs & a, const SmemPlan & sp)
+{
+  k_inflate<CR><<<grid, THREADS, smem, stream>>>(a, sp);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -234,9 +301,14 @@ int launch(
   a.radius = static_cast<int>(h->radius);
   a.inflate_unknown = h->cfg.inflate_unknown;
   a.inflate_around_unknown = h->cfg.inflate_around_unknown;
+  a.aligned_rows = (reinterpret_cast<uintptr_t>(d_master) % 4 == 0 && map_stride % 4 == 0 && size_x % 4 == 0) ? 1 : 0;
   const dim3 grid((w.max_i - w.min_i + TILE_W - 1) / TILE_W, (w.max_j - w.min_j + TILE_H - 1) / TILE_H, n_maps);
-  k_inflate<<<grid, THREADS, h->plan.total, stream>>>(a, h->plan);
-  INFL_CU(h, cudaGetLastError());
+  // the radii of nav2's defaults (0.55 m and 0.70 m at 0.05 m per cell) are compiled in; any other goes through a.radius
+  switch (h->radius) {
+    case 11: INFL_CU(h, launch_inflate<11>(grid, h->plan.total, stream, a, h->plan)); break;
+    case 14: INFL_CU(h, launch_inflate<14>(grid, h->plan.total, stream, a, h->plan)); break;
+    default: INFL_CU(h, launch_inflate<0>(grid, h->plan.total, stream, a, h->plan)); break;
+  }
   ++h->launches;
   return COSTMAP_INFLATION_OK;
 }
@@ -291,7 +363,7 @@ int costmap_inflation_create(const CostmapInflationConfig * config, CostmapInfla
   if (e != cudaSuccess) {return fail(e, "table");}
   e = cudaMemcpy(h->d_cost_by_sq, h->cost_by_sq.data(), h->cost_by_sq.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {return fail(e, "table copy");}
-  e = cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->plan.total));
+  e = cudaFuncSetAttribute(k_inflate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h->plan.total));
   if (e != cudaSuccess) {return fail(e, "shared memory");}
   *out = h;
   return COSTMAP_INFLATION_OK;

@@ -46,7 +46,7 @@ def test_whole_map_matches_oracle(shape, flags):
     assert layer.launch_count == 1
 
 
-@pytest.mark.parametrize("radius_m,resolution", [(0.05, 0.05), (0.12, 0.05), (1.0, 0.025), (3.0, 0.025), (4.1, 1.0), (2.0, 0.05)])
+@pytest.mark.parametrize("radius_m,resolution", [(0.05, 0.05), (0.55, 0.05), (0.12, 0.05), (1.0, 0.025), (3.0, 0.025), (4.1, 1.0), (2.0, 0.05)])
 def test_radii_from_one_cell_to_the_maximum(radius_m, resolution):
     rng = np.random.default_rng(int(radius_m * 1000))
     layer, cfg = make_layer(resolution, 0.3 * radius_m, inflation_radius=radius_m, cost_scaling_factor=2.0)
