@@ -250,6 +250,10 @@ _LIB = None
 
 
 def library_path() -> str:
+    """The in-tree library; MPPI_B200_LIBRARY points experiments at another build of the same sources."""
+    override = os.environ.get("MPPI_B200_LIBRARY")
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmppi_b200.so")
 
 
