@@ -424,6 +424,8 @@ def run_ours(args):
 
     if rank == 0 and not args.no_large_batch and args.workload == "c1":
         line["roofline_large_batch"] = large_batch_roofline(peak, peak_src, stream, flush)
+    if rank == 0 and not args.no_large_batch and args.workload == "c1":
+        line["costmap_inflation"] = inflation_pass(wl, peak, peak_src)
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl)
     if rank == 0:
@@ -431,6 +433,46 @@ def run_ours(args):
     opt.shutdown()
     if distributed:
         dist.destroy_process_group()
+
+
+def inflation_pass(wl, peak, peak_src):
+    """SURVEY.md section 8f row 3, reported beside the headline: the costmap inflation kernel (k_inflate) on the
+    workload's own 400x400 map reduced to its lethal cells, and on one GPU's share of the fleet (512 maps of
+    200x200).  Kernel time from CUDA events inside the library, L2 flushed before every pass; algorithmic bytes =
+    every cell read once + every changed cell written once.  A failure is reported, not hidden."""
+    try:
+        from navigation2_b200 import inflation, scenarios as S
+        kw = dict(inflation_radius=0.70, cost_scaling_factor=3.0)
+        layer = inflation.InflationLayer(wl["resolution"], 0.22, **kw)
+        out = {"kernel": "k_inflate<14>", "bound": "issue (ncu: issue slots ~80% busy; HBM fraction reported for scale)",
+               "peak": peak, "unit": "GB/s", "peak_source": peak_src, "cases": []}
+        cells = np.asarray(wl["cells"], dtype=np.uint8)
+        one = np.where(cells == 254, 254, 0).astype(np.uint8)[None]
+        fleet = np.stack([np.where(S.block_costmap(200, 200, 0.05, seed=100 + k, n_blocks=8) == 254, 254, 0).astype(np.uint8)
+                          for k in range(8)])
+        fleet = np.concatenate([fleet] * 64)  # 512 maps
+        for name, maps, steps in (("C1 map 400x400", one, 200), ("fleet share 512 x 200x200", fleet, 30)):
+            before = maps.copy()
+            ms = layer.time_resident(maps, steps=steps, warmup=3, flush_bytes=256 << 20)
+            probe = before[0].copy()
+            layer.updateCosts(probe, 0, 0, probe.shape[1], probe.shape[0])
+            changed = int((probe != before[0]).sum())
+            if maps.shape[0] > 1:
+                changed = 0
+                for k in range(8):
+                    probe = before[k].copy()
+                    layer.updateCosts(probe, 0, 0, probe.shape[1], probe.shape[0])
+                    changed += int((probe != before[k]).sum())
+                changed *= maps.shape[0] // 8
+            alg = int(maps.size) + changed
+            out["cases"].append({"workload": name, "kernel_ms": ms, "cells_per_s": maps.size / (ms * 1e-3),
+                                 "algorithmic_bytes_per_launch": alg, "achieved": alg / (ms * 1e-3) / 1e9,
+                                 "frac": alg / (ms * 1e-3) / 1e9 / peak})
+        out["gpu_launches"] = layer.launch_count
+        layer.close()
+        return out
+    except Exception as exc:  # the headline line must still be printed
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 def large_batch_roofline(peak, peak_src, stream, flush):
