@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
 {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_row_has_seed[TILE_H / 2];
+  __shared__ int s_word_has_seed[(TILE_W + 2 * COSTMAP_INFLATION_MAX_CELL_RADIUS + 6) / 4 + 1];  // per 4 staged columns
+  __shared__ int s_col_lo, s_col_hi;  // staged columns that hold a squared distance below FAR_SQ
   uint8_t * s_raw = smem + sp.off_raw;
   uint8_t * s_up = smem + sp.off_up;
   uint32_t * s_sq = reinterpret_cast<uint32_t *>(smem + sp.off_sq);
@@ -105,6 +107,10 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
   const int xa = words ? ((x0 - R) & ~3) : (x0 - R);
   const int shift = (x0 - R) - xa;
   unsigned seen_seed = 0;
+  for (int i = tid; i < (region_w + 6) / 4 + 1; i += NT) {s_word_has_seed[i] = words ? 0 : 1;}
+  if (tid < TILE_H / 2) {s_row_has_seed[tid] = 0;}
+  if (tid == 0) {s_col_lo = region_w; s_col_hi = -1;}
+  __syncthreads();
   if (words) {
     const int n_words = (region_w + shift + 3) >> 2;
     // a byte is a seed iff (byte & keep) == 0xFE: keep = 0xFF matches 254 only, keep = 0xFE matches 254 and 255
@@ -117,6 +123,7 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
       uint32_t * dst = reinterpret_cast<uint32_t *>(s_raw + warp * sp.raw_pitch) + w;
       const size_t src_step = static_cast<size_t>(NT / 32) * a.size_x;
       const int dst_step = (NT / 32) * (sp.raw_pitch >> 2);
+      unsigned word_seen = 0u;
 #pragma unroll 4
       for (int ry = warp; ry < region_h; ry += NT / 32) {
         uint32_t cells = 0u;
@@ -125,9 +132,11 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
         }
         *dst = cells;
         const unsigned v = (cells ^ 0xFEFEFEFEu) & keep;             // zero byte <=> seed
-        seen_seed |= (v - 0x01010101u) & ~v & 0x80808080u;           // non-zero iff some byte of v is zero
+        word_seen |= (v - 0x01010101u) & ~v & 0x80808080u;           // non-zero iff some byte of v is zero
         gy += NT / 32; src += src_step; dst += dst_step;
       }
+      seen_seed |= word_seen;
+      if (word_seen != 0u) {s_word_has_seed[w] = 1;}
     }
   } else {
     for (int ry = warp; ry < region_h; ry += NT / 32) {
@@ -143,7 +152,6 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
       }
     }
   }
-  if (tid < TILE_H / 2) {s_row_has_seed[tid] = 0;}
   if (!__syncthreads_or(seen_seed != 0u)) {return;}  // nothing within R of this tile: every cell is skipped (:259-261)
   for (int i = tid; i <= R * R; i += NT) {s_lut[i] = __ldg(a.cost_by_sq + i);}
   if (CR == 0) {
@@ -159,6 +167,14 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
   uint16_t * s_sq16 = reinterpret_cast<uint16_t *>(s_sq);
   const unsigned far_start = 2u * COSTMAP_INFLATION_MAX_CELL_RADIUS + TILE_H + 8u;  // larger than any reachable distance
   for (int col = tid; col < region_w; col += NT) {
+    if (!s_word_has_seed[(col + shift) >> 2]) {  // no seed in these four staged columns: nothing to sweep
+#pragma unroll 4
+      for (int r = 0; r < TILE_H; ++r) {
+        s_sq16[(((r & (TILE_H / 2 - 1)) * sp.g_pitch + col) << 1) + (r >> 4)] = static_cast<uint16_t>(FAR_SQ);
+      }
+      continue;
+    }
+    bool column_near = false;
     const uint8_t * cell = s_raw + (region_h - 1) * sp.raw_pitch + col + shift;
     unsigned dist = far_start;
     for (int i = 0; i < R; ++i) {  // halo below the tile
@@ -187,8 +203,13 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
       const bool near = g <= static_cast<unsigned>(R);
       s_sq16[(((r & (TILE_H / 2 - 1)) * sp.g_pitch + col) << 1) + (r >> 4)] = static_cast<uint16_t>(near ? g * g : FAR_SQ);
       if (near) {s_row_has_seed[r & (TILE_H / 2 - 1)] = 1;}
+      column_near |= near;
       cell += sp.raw_pitch;
       up += sp.g_pitch;
+    }
+    if (column_near) {
+      atomicMin(&s_col_lo, col);
+      atomicMax(&s_col_hi, col);
     }
   }
   __syncthreads();
@@ -199,7 +220,8 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
   const int gx = x0 + c;
   const unsigned r_sq = static_cast<unsigned>(R * R);
   const bool inflate_unknown = a.inflate_unknown != 0;
-  if (gx >= a.max_i) {return;}
+  // the taps of this cell are staged columns c .. c + 2R: none of them is near a seed -> every row of it is skipped
+  if (gx >= a.max_i || c + 2 * R < s_col_lo || c > s_col_hi) {return;}
   for (int r = tid / TILE_W; r < TILE_H / 2; r += (NT / TILE_W)) {
     if (!s_row_has_seed[r]) {continue;}
     const uint32_t * row = s_sq + r * sp.g_pitch + c;  // row[k] is column gx - R + k
