@@ -73,7 +73,9 @@ def build_host(force: bool = False, verbose: bool = False) -> str:
     and its test driver.  Built against the in-tree ROS type shim; with a ROS 2 underlay it is built by colcon."""
     src = os.path.join(HOST, "src", "mppi.cpp")
     hdrs = [os.path.join(HOST, "include", "nav2_mppi_controller_b200", "mppi.hpp"),
-            os.path.join(HOST, "include", "ros_shim", "ros_shim.hpp"), os.path.join(ROOT, "include", "mppi_b200.h")]
+            os.path.join(HOST, "include", "ros_shim", "ros_shim.hpp"), os.path.join(ROOT, "include", "mppi_b200.h"),
+            os.path.join(HOST, "include", "nav2_costmap_2d_b200", "inflation_layer.hpp"),
+            os.path.join(ROOT, "include", "costmap_inflation_b200.h")]
     test_src = os.path.join(HOST, "test", "test_host.cpp")
     inc = ["-I", os.path.join(HOST, "include"), "-I", os.path.join(ROOT, "include")]
     common = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-fPIC", *inc]

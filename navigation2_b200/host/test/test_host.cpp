@@ -4,11 +4,13 @@
 // reference's controller_state_transition_test.cpp and optimizer_smoke_test.cpp.
 //   test_host config            parameter parsing / exceptions only (no GPU needed)
 //   test_host run <model> <n>   n closed-loop cycles on the GPU; prints "cmd vx vy wz" per cycle
+//   test_host inflate           the InflationLayer mirror on the GPU: the cases of inflation_tests.cpp, prints the grids
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 
+#include "nav2_costmap_2d_b200/inflation_layer.hpp"
 #include "nav2_mppi_controller_b200/mppi.hpp"
 
 namespace
@@ -158,10 +160,65 @@ int testRun(const std::string & model, int cycles)
 }
 }  // namespace
 
+// nav2_costmap_2d/test/integration/inflation_tests.cpp:233-258, :330-381 through the C++ mirror; the grids are
+// printed row by row ("grid <name> <sx> <sy>" then sy lines) so the Python test can compare them with the oracle
+int testInflate()
+{
+  using nav2_costmap_2d::Costmap2D;
+  using nav2_costmap_2d::InflationLayer;
+  auto dump = [](const char * name, const Costmap2D & m) {
+      std::printf("grid %s %u %u\n", name, m.getSizeInCellsX(), m.getSizeInCellsY());
+      for (unsigned int y = 0; y < m.getSizeInCellsY(); ++y) {
+        for (unsigned int x = 0; x < m.getSizeInCellsX(); ++x) {std::printf("%u ", m.getCost(x, y));}
+        std::printf("\n");
+      }
+    };
+  {
+    InflationLayer::Parameters p;
+    p.inflation_radius = 4.1; p.cost_scaling_factor = 1.0;
+    InflationLayer layer(p);
+    Costmap2D grid(10, 10, 1.0, 0.0, 0.0, 0);
+    layer.matchSize(grid);
+    layer.onFootprintChanged(2.1);
+    grid.setCost(0, 0, nav2_costmap_2d::LETHAL_OBSTACLE);
+    layer.updateCosts(grid, 0, 0, 10, 10);
+    if (layer.getCellInflationRadius() != 5 || grid.getCost(0, 0) != 254 || grid.getCost(2, 0) != 253) {return 1;}
+    dump("corner", grid);
+  }
+  {
+    InflationLayer::Parameters p;
+    p.inflation_radius = 10.5; p.cost_scaling_factor = 1.0;
+    InflationLayer layer(p);
+    Costmap2D grid(100, 100, 1.0, 0.0, 0.0, 0);
+    layer.matchSize(grid);
+    layer.onFootprintChanged(5.0);
+    grid.setCost(50, 50, nav2_costmap_2d::LETHAL_OBSTACLE);
+    layer.updateCosts(grid, 0, 0, 100, 100);
+    for (unsigned int i = 6; i <= 11; ++i) {
+      if (grid.getCost(50 + i, 50) != layer.computeCost(static_cast<double>(i))) {return 2;}  // :362-365
+    }
+    dump("centre", grid);
+  }
+  {
+    InflationLayer::Parameters p;  // nav2 defaults on a bring-up sized map, window update
+    p.inflation_radius = 0.70; p.cost_scaling_factor = 3.0;
+    InflationLayer layer(p);
+    Costmap2D grid(200, 120, 0.05, 0.0, 0.0, 0);
+    layer.matchSize(grid);
+    layer.onFootprintChanged(0.22);
+    for (unsigned int k = 0; k < 40; ++k) {grid.setCost((k * 37) % 200, (k * 53) % 120, nav2_costmap_2d::LETHAL_OBSTACLE);}
+    layer.updateCosts(grid, 20, 10, 180, 100);
+    dump("window", grid);
+  }
+  std::printf("inflate ok\n");
+  return 0;
+}
+
 int main(int argc, char ** argv)
 {
   try {
     if (argc >= 2 && std::strcmp(argv[1], "config") == 0) {return testConfig();}
+    if (argc >= 2 && std::strcmp(argv[1], "inflate") == 0) {return testInflate();}
     if (argc >= 4 && std::strcmp(argv[1], "run") == 0) {return testRun(argv[2], std::atoi(argv[3]));}
   } catch (const std::exception & e) {
     std::printf("EXCEPTION: %s\n", e.what());

@@ -69,3 +69,33 @@ def test_controller_lifecycle_on_gpu_matches_python_binding(model):
         y += (speed[0] * np.sin(yaw) + speed[1] * np.cos(yaw)) * 0.05
         yaw += speed[2] * 0.05
     opt.shutdown()
+
+
+@pytest.mark.gpu
+def test_inflation_layer_mirror_on_gpu_matches_oracle():
+    """navigation2_b200/host/include/nav2_costmap_2d_b200/inflation_layer.hpp driven like the reference's
+    inflation_tests.cpp; every printed grid is compared with the CPU oracle."""
+    from oracle import inflation_binding as ob
+    out = subprocess.run([BIN, "inflate"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "inflate ok" in out.stdout
+    lines = out.stdout.splitlines()
+    grids = {}
+    i = 0
+    while i < len(lines):
+        if lines[i].startswith("grid "):
+            _, name, sx, sy = lines[i].split()
+            rows = [[int(v) for v in lines[i + 1 + r].split()] for r in range(int(sy))]
+            grids[name] = np.array(rows, dtype=np.uint8)
+            assert grids[name].shape == (int(sy), int(sx))
+            i += int(sy)
+        i += 1
+    seed = np.zeros((10, 10), np.uint8); seed[0, 0] = 254
+    assert np.array_equal(grids["corner"], ob.update_costs(ob.config(1.0, 2.1, inflation_radius=4.1, cost_scaling_factor=1.0), seed))
+    seed = np.zeros((100, 100), np.uint8); seed[50, 50] = 254
+    assert np.array_equal(grids["centre"], ob.update_costs(ob.config(1.0, 5.0, inflation_radius=10.5, cost_scaling_factor=1.0), seed))
+    seed = np.zeros((120, 200), np.uint8)
+    for k in range(40):
+        seed[(k * 53) % 120, (k * 37) % 200] = 254
+    want = ob.update_costs(ob.config(0.05, 0.22, inflation_radius=0.70, cost_scaling_factor=3.0), seed, 20, 10, 180, 100)
+    assert np.array_equal(grids["window"], want)
