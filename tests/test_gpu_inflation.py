@@ -171,6 +171,26 @@ def test_large_grids_take_the_small_cta_path(radius_m):
     assert np.array_equal(got, ob.update_costs(cfg, grid))
 
 
+def test_kernel_agrees_with_reference_golden():
+    """Distances produced by the REFERENCE's own distance transform (tests/golden/inflation_reference_dt.npz) decide
+    the expected cost of every cell through the reference's table chain; the kernel must reproduce them."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inflation_reference_dt.npz"))
+    layer, cfg = make_layer(0.05, 0.22, inflation_radius=0.70, cost_scaling_factor=3.0)
+    lut = layer.cost_lut()
+    radius = float(layer.cell_inflation_radius)
+    for n in sorted({k.split("__")[0] for k in gold.files}):
+        mask, dist = gold[f"{n}__mask"], gold[f"{n}__distance"]
+        grid = np.where(mask != 0, LETHAL, 0).astype(np.uint8)
+        got = grid.copy()
+        layer.updateCosts(got, 0, 0, grid.shape[1], grid.shape[0])
+        # applyInflation (inflation_layer.cpp:259-276) on the reference's distances, old cost 0 or LETHAL
+        near = np.minimum(dist, np.float32(radius + 1.0))  # cells beyond the radius are skipped anyway (:259-261)
+        slot = np.minimum(len(lut) - 1, (near * np.float32(100) + np.float32(0.5)).astype(np.uint32))
+        want = np.where(dist > radius, grid, np.maximum(grid, lut[slot]))
+        assert np.array_equal(got, want), n
+
+
 def test_errors_and_degenerate_radius():
     with pytest.raises(ValueError):
         infl.InflationLayer(0.01, 0.2, inflation_radius=5.0)  # 500 cells

@@ -44,6 +44,16 @@ def test_distance_map_matches_the_reference_header_bit_for_bit():
         assert np.array_equal(ob.distance_map(mask), ob.distance_map(mask, ref=True)), shape
 
 
+def test_distance_map_matches_reference_golden():
+    """tests/golden/inflation_reference_dt.npz holds outputs of the reference's own distanceTransform2D
+    (tests/golden/make_inflation_golden.py): the pin that travels to boxes without /root/reference."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "inflation_reference_dt.npz"))
+    names = sorted({k.split("__")[0] for k in gold.files})
+    assert len(names) == 6
+    for n in names:
+        assert np.array_equal(ob.distance_map(gold[f"{n}__mask"]), gold[f"{n}__distance"]), n
+
+
 def test_cell_distance_and_cost_table():
     # costmap_2d.cpp:254-258 and inflation_layer.cpp:351-366 / inflation_layer.hpp:121-135
     cfg = ob.config(resolution=0.05, inscribed_radius=0.22, inflation_radius=0.70, cost_scaling_factor=3.0)
