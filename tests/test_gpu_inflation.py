@@ -155,9 +155,9 @@ def test_large_map_matches_oracle_and_is_idempotent():
     assert np.array_equal(out[1000:1400, 2000:2400], ob.update_costs(cfg, big[900:1500, 1900:2500])[100:500, 100:500])
 
 
-@pytest.mark.parametrize("radius_m", [0.55, 0.70, 2.0])
+@pytest.mark.parametrize("radius_m", [0.55, 0.70, 1.0, 1.6, 2.0])
 def test_large_grids_take_the_small_cta_path(radius_m):
-    # >= 2368 tiles: 128-thread CTAs (compiled-in radii 11 and 14, and the generic radius path)
+    # >= 2368 tiles: 128 x 64 tiles up to 32 cells of radius (compiled-in 11 and 14, generic 20 and 32), 128-thread CTAs beyond
     rng = np.random.default_rng(int(radius_m * 100))
     layer, cfg = make_layer(0.05, 0.22, inflation_radius=radius_m, cost_scaling_factor=3.0, inflate_around_unknown=True)
     grid = random_grid(rng, (2048, 3072), lethal=0.0006, unknown=0.0003, costs=0.01)
