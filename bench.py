@@ -422,11 +422,11 @@ def run_ours(args):
         "clocks": clocks,
     }
 
-    if rank == 0 and not args.no_large_batch and args.workload == "c1":
+    # single-GPU extras (rank 0 at N = 1 only): the HBM-regime kernels, the inflation pass, the CPU baseline
+    if rank == 0 and world == 1 and not args.no_large_batch and args.workload == "c1":
         line["roofline_large_batch"] = large_batch_roofline(peak, peak_src, stream, flush)
-    if rank == 0 and not args.no_large_batch and args.workload == "c1":
         line["costmap_inflation"] = inflation_pass(wl, peak, peak_src)
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl)
     if rank == 0:
         emit(line)

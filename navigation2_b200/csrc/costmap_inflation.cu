@@ -165,12 +165,16 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
   //      the tile, then the tile rows), then to the nearest seed above (down sweep), combined into squared column
   //      distances (FAR_SQ beyond R); tile rows r and r + 16 share one 32-bit word ----
   uint16_t * s_sq16 = reinterpret_cast<uint16_t *>(s_sq);
-  const unsigned far_start = 2u * COSTMAP_INFLATION_MAX_CELL_RADIUS + TILE_H + 8u;  // larger than any reachable distance
+  // "no seed yet": with a compiled-in radius the sweeps stay far below 256 and need no clamp before the byte store
+  const unsigned far_start = CR > 0 ? static_cast<unsigned>(CR) + 1u : 2u * COSTMAP_INFLATION_MAX_CELL_RADIUS + TILE_H + 8u;
   for (int col = tid; col < region_w; col += NT) {
     if (!s_word_has_seed[(col + shift) >> 2]) {  // no seed in these four staged columns: nothing to sweep
+      uint16_t * sq = s_sq16 + (col << 1);
 #pragma unroll 4
-      for (int r = 0; r < TILE_H; ++r) {
-        s_sq16[(((r & (TILE_H / 2 - 1)) * sp.g_pitch + col) << 1) + (r >> 4)] = static_cast<uint16_t>(FAR_SQ);
+      for (int r = 0; r < TILE_H / 2; ++r) {
+        sq[0] = static_cast<uint16_t>(FAR_SQ);
+        sq[1] = static_cast<uint16_t>(FAR_SQ);
+        sq += 2 * sp.g_pitch;
       }
       continue;
     }
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
 #pragma unroll 4
     for (int i = 0; i < TILE_H; ++i) {
       dist = (static_cast<unsigned>(*cell) - 254u <= seed_span) ? 0u : dist + 1u;
-      *up = static_cast<uint8_t>(min(dist, 255u));
+      *up = static_cast<uint8_t>(CR > 0 ? dist : min(dist, 255u));
       cell -= sp.raw_pitch;
       up -= sp.g_pitch;
     }
@@ -196,16 +200,24 @@ __global__ void __launch_bounds__(NT) k_inflate(const InflateArgs a, const SmemP
       cell += sp.raw_pitch;
     }
     up = s_up + col;
+    // tile rows r and r + TILE_H / 2 are the two halves of word (r, col): one running pointer per half
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint16_t * sq = s_sq16 + (col << 1) + half;
+      int * row_flag = s_row_has_seed;
 #pragma unroll 4
-    for (int r = 0; r < TILE_H; ++r) {
-      dist = (static_cast<unsigned>(*cell) - 254u <= seed_span) ? 0u : dist + 1u;
-      const unsigned g = min(dist, static_cast<unsigned>(*up));
-      const bool near = g <= static_cast<unsigned>(R);
-      s_sq16[(((r & (TILE_H / 2 - 1)) * sp.g_pitch + col) << 1) + (r >> 4)] = static_cast<uint16_t>(near ? g * g : FAR_SQ);
-      if (near) {s_row_has_seed[r & (TILE_H / 2 - 1)] = 1;}
-      column_near |= near;
-      cell += sp.raw_pitch;
-      up += sp.g_pitch;
+      for (int r = 0; r < TILE_H / 2; ++r) {
+        dist = (static_cast<unsigned>(*cell) - 254u <= seed_span) ? 0u : dist + 1u;
+        const unsigned g = min(dist, static_cast<unsigned>(*up));
+        const bool near = g <= static_cast<unsigned>(R);
+        *sq = static_cast<uint16_t>(near ? g * g : FAR_SQ);
+        if (near) {*row_flag = 1;}
+        column_near |= near;
+        cell += sp.raw_pitch;
+        up += sp.g_pitch;
+        sq += 2 * sp.g_pitch;
+        ++row_flag;
+      }
     }
     if (column_near) {
       atomicMin(&s_col_lo, col);
