@@ -500,8 +500,8 @@ def large_batch_roofline(peak, peak_src, stream, flush):
            "kernel": "k_rollout_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
            "frac": achieved / peak, "traffic": measured_traffic("k_rollout_score@2^20x56"),
            "algorithmic_bytes_per_launch": alg, "kernel_ms": ka_ms, "launches_timed": ka_n, "peak_source": peak_src,
-           "limiter": "instruction issue (ncu: issue slots ~73% busy at 172 instructions per trajectory-step: IEEE sqrt, "
-                      "two IEEE divisions per costmap lookup, sin/cos per step), not HBM",
+           "limiter": "instruction issue (ncu: issue slots ~72% busy at 169 instructions per trajectory-step: IEEE sqrt, "
+                      "sin/cos per step, costmap lookups), not HBM",
            "kernel_c": {"kernel": "k_softmax_partial", "bound": "hbm", "achieved": achieved_c, "peak": peak, "unit": "GB/s",
                         "frac": achieved_c / peak, "traffic": measured_traffic("k_softmax_partial@2^20x56"),
                         "algorithmic_bytes_per_launch": alg_c, "kernel_ms": kc_ms, "launches_timed": kc_n},
