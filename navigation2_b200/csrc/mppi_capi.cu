@@ -142,7 +142,8 @@ struct MppiHandle
   int32_t * d_xerror = nullptr, * h_xerror = nullptr;
   bool peers_open = false;
   int shard_iteration = 0;                // iterations launched since mppi_shard_begin
-  uint32_t xseq = 0;                      // exchanges performed (sequence number = xseq + 1, parity = xseq & 1)
+  uint32_t xseq[2] = {0, 0};              // exchanges performed per kind (sequence number = xseq + 1, parity = xseq & 1)
+  bool shard_failed = false;              // an exchange timed out: the ranks are out of step for good, the handle is dead
   uint8_t * d_flush = nullptr;    // mppi_time_resident: the buffer overwritten to flush L2
   size_t flush_bytes = 0;
   std::vector<cudaEvent_t> resident_events;
@@ -1328,6 +1329,14 @@ int mppi_set_config(MppiHandle * h, const MppiConfig * cfg)
   }
   CU_CHECK(h, cudaStreamSynchronize(h->stream));
   const MppiConfig old = h->cfg;
+  if (h->d_mailbox &&
+    (cfg->time_steps != old.time_steps || cfg->shard_world != old.shard_world || cfg->shard_rank != old.shard_rank))
+  {
+    // the mailbox layout (slot stride, peers' IPC mappings) was exchanged for the old shape: a peer writing a larger
+    // payload at the old stride would overrun its neighbour's slot
+    h->error = "time_steps / shard_world / shard_rank cannot change once the exchange mailbox exists: create a new handle";
+    return MPPI_ERR_UNSUPPORTED;
+  }
   std::string err;
   int rc = validate_and_derive(h, *cfg, err);
   if (rc != MPPI_OK) {
@@ -2182,16 +2191,23 @@ int enqueue_exchange(MppiHandle * h, int kind)
   x.peers = h->d_peers;
   x.world = static_cast<int32_t>(h->cfg.shard_world); x.rank = static_cast<int32_t>(h->cfg.shard_rank);
   x.kind = kind;
-  x.parity = static_cast<int32_t>(h->xseq & 1u);
-  x.seq = h->xseq + 1u;
+  // each kind has its own sequence counter and its own pair of payload buffers: exchange n + 1 of a kind writes the
+  // buffer exchange n did not use, and a rank can only start n + 2 after every peer has published n + 1, i.e. after
+  // every peer has finished reading n — whatever the order in which the two kinds are called
+  x.parity = static_cast<int32_t>(h->xseq[kind] & 1u);
+  x.seq = h->xseq[kind] + 1u;
   x.payload_base = kind == 0 ? h->mailbox_words_base : h->mailbox_slots_base;
   x.payload_stride = kind == 0 ? h->mailbox_words_stride : h->mailbox_slots_stride;
   x.n_words = kind == 0 ? RED_WORDS * h->R : (2 + 3 * h->T) * h->R;
+  if (static_cast<size_t>(x.n_words) * 4u > x.payload_stride) {
+    h->error = "exchange payload larger than the mailbox slot (time_steps changed on a live sharded handle?)";
+    return MPPI_ERR_INVALID_ARGUMENT;
+  }
   x.src = reinterpret_cast<const uint32_t *>(kind == 0 ? static_cast<void *>(h->d_red) : static_cast<void *>(h->d_slot));
   x.dst = reinterpret_cast<uint32_t *>(kind == 0 ? static_cast<void *>(h->d_red) : static_cast<void *>(h->d_slot_all));
   x.error = h->d_xerror;
   CU_CHECK(h, mppi_launch_shard_exchange(x, h->stream));
-  h->xseq++;
+  h->xseq[kind]++;
   h->launches++;
   return MPPI_OK;
 }
@@ -2284,6 +2300,10 @@ int mppi_shard_cycle(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
 {
   if (!h || !in || !out) {return MPPI_ERR_INVALID_ARGUMENT;}
   if (!h->peers_open && h->cfg.shard_world > 1) {h->error = "mppi_shard_cycle needs mppi_shard_open_peers first"; return MPPI_ERR_NOT_READY;}
+  if (h->shard_failed) {
+    h->error = "an earlier exchange timed out: the ranks are out of step, destroy and re-create the sharded handles";
+    return MPPI_ERR_CUDA;
+  }
   const auto ht0 = std::chrono::steady_clock::now();
   int rc = mppi_shard_begin(h, in);
   if (rc != MPPI_OK) {return rc;}
@@ -2312,7 +2332,12 @@ int mppi_shard_cycle(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
     break;
   }
   if (h->h_xerror && *static_cast<volatile int32_t *>(h->h_xerror)) {
-    h->error = "a peer did not reach an exchange within 2 s";
+    // The kernels after a timed-out exchange ran on stale payloads and committed their result on this rank, and the
+    // peers are one exchange out of step: nothing on this handle can be trusted any more.  It is marked dead (every
+    // later cycle fails at once instead of waiting 2 s per exchange); the caller re-creates the handles on all ranks.
+    *h->h_xerror = 0;
+    h->shard_failed = true;
+    h->error = "a peer did not reach an exchange within 2 s; the sharded handle is dead, re-create it on every rank";
     return MPPI_ERR_CUDA;
   }
   return MPPI_OK;

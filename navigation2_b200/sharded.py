@@ -6,7 +6,7 @@ not depend on the number of ranks.
   kernel A (rollout + per-trajectory critics)
   all-reduce MAX over the 8 reduction words      furthest path point, -min repulsion, any-free flags
   kernels B, C, D1 (path critics, local softmax partials, local (min, sum, W) slot)
-  all-gather of the (2 + 3T)-float slots          rescaled by exp(-(m_g - m)/temperature) in kernel D2
+  all-gather of the (2 + 3T)-float slots          rescaled by exp(-(m - m_g)/temperature) <= 1 in kernel D2 (m: the rank's min, m_g: the global min)
   kernel D2 (combine, Savitzky-Golay filter, constraints, validator) — run redundantly on every rank
 """
 from __future__ import annotations
@@ -47,13 +47,7 @@ class ShardedOptimizer(Optimizer):
         cur = torch.cuda.current_stream()
         self._stream = cur if cur.cuda_stream != 0 else torch.cuda.Stream()
         _raise_for(self._lib, self._h, self._lib.mppi_set_stream(self._h, self._stream.cuda_stream))
-        ar1, slot, slot_all = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        n1, n2 = C.c_size_t(), C.c_size_t()
-        _raise_for(self._lib, self._h, self._lib.mppi_shard_buffers(
-            self._h, C.byref(ar1), C.byref(n1), C.byref(slot), C.byref(n2), C.byref(slot_all)))
-        self._ar1 = torch.as_tensor(_DeviceBuffer(ar1.value, n1.value, "<i4"), device="cuda")
-        self._slot = torch.as_tensor(_DeviceBuffer(slot.value, n2.value, "<f4"), device="cuda")
-        self._slot_all = torch.as_tensor(_DeviceBuffer(slot_all.value, n2.value * self.world, "<f4"), device="cuda")
+        self._bind_exchange_buffers()
         # Exchanges over peer memory (k_shard_exchange): every rank exports its mailbox as a CUDA IPC handle, the
         # handles are all-gathered once, and from then on a cycle never goes through the host between its kernels.
         # MPPI_B200_NCCL_EXCHANGE=1 keeps the torch.distributed collectives between the kernels (A/B measurements).
@@ -68,6 +62,26 @@ class ShardedOptimizer(Optimizer):
             _raise_for(self._lib, self._h, self._lib.mppi_shard_open_peers(self._h, handles))
             dist.barrier(group=group)      # every mailbox is open everywhere before the first exchange
             self._peer_exchange = True
+
+    def _bind_exchange_buffers(self) -> None:
+        """Views of the library's exchange buffers for the torch.distributed collectives.  The library re-allocates
+        them whenever the configuration is set (mppi_set_config -> allocate), so the views are rebuilt then."""
+        torch = self._torch
+        ar1, slot, slot_all = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n1, n2 = C.c_size_t(), C.c_size_t()
+        _raise_for(self._lib, self._h, self._lib.mppi_shard_buffers(
+            self._h, C.byref(ar1), C.byref(n1), C.byref(slot), C.byref(n2), C.byref(slot_all)))
+        self._ar1 = torch.as_tensor(_DeviceBuffer(ar1.value, n1.value, "<i4"), device="cuda")
+        self._slot = torch.as_tensor(_DeviceBuffer(slot.value, n2.value, "<f4"), device="cuda")
+        self._slot_all = torch.as_tensor(_DeviceBuffer(slot_all.value, n2.value * self.world, "<f4"), device="cuda")
+
+    def setConfig(self, cfg: capi.MppiConfig) -> None:
+        """Dynamic parameter update of a live sharded handle.  The shard layout (shard_world, shard_rank, time_steps)
+        is fixed once the peers' mailboxes are open: the library rejects a change (MPPI_ERR_UNSUPPORTED)."""
+        if int(cfg.n_robots) != 1 or int(cfg.shard_world) != self.world:
+            raise ValueError("n_robots / shard_world cannot change on a live sharded handle")
+        super().setConfig(cfg)
+        self._bind_exchange_buffers()
 
     def evalControl(self, inp: CycleInput, raise_on_failure: bool = True) -> CycleResult:
         lib, h = self._lib, self._h
@@ -160,7 +174,8 @@ def local_slot(costs: np.ndarray, cv: np.ndarray, inv_temp: float) -> np.ndarray
 
 def combine_slots(slots: np.ndarray, inv_temp: float) -> np.ndarray:
     """All-gathered slots (world, 2 + 3T) -> softmax-weighted mean control sequence (3T,),
-    rescaling every rank by exp(-(m_g - m)/temperature) (kernel D2)."""
+    rescaling every rank by exp(-(m - m_g)/temperature) <= 1, m the rank's own minimum and m_g the
+    global one (kernel D2)."""
     slots = np.asarray(slots, dtype=np.float32)
     m = slots[:, 0].min()
     scale = np.exp(-np.float32(inv_temp) * (slots[:, 0] - m)).astype(np.float64)
