@@ -4,20 +4,27 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c3|c4|c5]
 
 A *step* is one Optimizer::optimize() (iteration_count iterations of rollout -> score -> update)
-over one batch of synthetic input.  Default workload (N=1): BASELINE.json configs[1], DiffDrive
-2000 x 56, model_dt 0.05, default critics with the bring-up yaml weights, 400x400 costmap @0.05 m,
-seeded injected noise.  N>1 (torchrun, one rank per GPU): every rank drives its own independent
-controller on the same workload — "fleets of independent controllers are partitioned one robot-set
-per GPU", no data-path collective, weak scaling.  `--workload c4` is the 1M x 56 batch sharded over
-the ranks with the NCCL exchanges of SURVEY.md §8e (strong scaling); `--workload c5` is the fleet.
+over one batch of synthetic input.  Headline workload: BASELINE.json configs[1], DiffDrive 2000 x 56,
+model_dt 0.05, default critics with the bring-up yaml weights, 400x400 costmap @0.05 m, seeded injected
+noise.  N>1 (torchrun, one rank per GPU): every rank drives its own independent controller on the same
+workload ("fleets of independent controllers are partitioned one robot-set per GPU", no data-path
+collective, weak scaling).
+
+The same JSON line carries, at EVERY N, the two multi-GPU workloads north_star names:
+  c4_sharded  BASELINE.json configs[3]: ONE 2^20 x 56 batch sharded along the trajectory axis over the N ranks
+              (strong scaling; the two exchanges of an iteration run over peer memory inside the kernels),
+              whole mppi_shard_cycle calls with host buffers, max over ranks, parity-checked against the oracle
+  c5_fleet    BASELINE.json configs[4]: 512 robots per GPU, own 200x200 costmap + path each (weak scaling),
+              device-timed and end to end, parity-checked against the oracle
+`--workload c3|c4|c5` makes one of them the headline line instead (development runs).
 
 Printed JSON (one line, rank 0):
   value      trajectory-steps/s, inputs resident in HBM, CUDA-event timed, L2 flushed between steps
-  e2e        the same metric through the public API (Optimizer.evalControl) with HOST buffers:
-             costmap + cycle inputs H2D from pinned memory and the command/control sequence D2H
-             inside the timed region
-  roofline   dominant kernel (rollout+score) against the measured HBM peak
-  cpu_baseline  the CPU oracle (a restatement, `kind: port`) on this box's host cores, 1 thread
+  e2e        the same metric through the C ABI (mppi_optimize_in_place) with HOST buffers: costmap window +
+             cycle inputs H2D from pinned memory and the command / control sequence D2H inside the timed region
+  roofline   dominant kernel against the measured HBM peak
+  cpu_baseline  the CPU oracle (a restatement, `kind: port`) on this box's host cores: 1 thread like the
+             reference's control path, plus an all-cores figure (one independent controller per core)
 """
 from __future__ import annotations
 
@@ -48,7 +55,7 @@ def parse_args():
     ap.add_argument("--workload", default="c1", choices=["c1", "c3", "c4", "c5"])
     ap.add_argument("--robots", type=int, default=512, help="robots per GPU for --workload c5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-large-batch", action="store_true")
+    ap.add_argument("--no-large-batch", action="store_true", help="skip roofline_large_batch / c4_sharded / c5_fleet")
     return ap.parse_args()
 
 
@@ -82,6 +89,31 @@ def workload_c3(model="omni"):
                         goal_checker_xy_tolerance=0.25)
     return dict(name=f"C3 {model} 16384x100, full critic set incl. Obstacles+inflation, 400x400 costmap",
                 cfg=cfg, cells=cells, resolution=0.05, origin=(0.0, 0.0), inp=inp, holo=model == "omni")
+
+
+def workload_reference_harness():
+    """The reference's own harness (benchmark/optimizer_benchmark.cpp:49-99): DiffDrive 2000 x 56, iteration_count 2,
+    40x40 costmap @0.1 m with one 8x8 block of cost 250, 50 path poses stepping (+0.1, +0.1)."""
+    from navigation2_b200 import params as P, scenarios as S
+    import navigation2_b200 as nb
+    cells, res, origin, path = S.reference_benchmark_fixture()
+    cfg = P.make_config({"batch_size": 2000, "time_steps": 56, "iteration_count": 2, "motion_model": "diff_drive"},
+                        P.NAV2_BRINGUP_CRITICS, robot_radius=0.15)
+    inp = nb.CycleInput(pose=(2.0, 2.0, 0.785), speed=(0.0, 0.0, 0.0), path=path, goal=tuple(path[-1]))
+    return dict(name="reference harness: DiffDrive 2000x56, iteration_count 2, 40x40 costmap @0.1 m (optimizer_benchmark.cpp)",
+                cfg=cfg, cells=cells, resolution=res, origin=origin, inp=inp, holo=False)
+
+
+def bench_config(wl, cfg):
+    """The `config` object of the JSON line.  Both arms build it here from the workload alone, so the driver's
+    same_config check compares like with like; arm-specific detail (L2 handling, parallelism) is spelled out for both
+    arms in the same strings."""
+    return {"workload": wl["name"], "batch_size": int(cfg.batch_size), "time_steps": int(cfg.time_steps),
+            "iteration_count": int(cfg.iteration_count),
+            "l2": "GPU arm: L2 flushed before every timed step (a 256 MiB buffer overwritten, mppi_time_resident); "
+                  "reference arm: CPU, caches as they fall",
+            "parallelism": "GPU arm: one independent controller per GPU, no collective (weak scaling), plus the c4_sharded / "
+                           "c5_fleet sections; reference arm: rank 0 only, single thread like the reference's control path"}
 
 
 def large_batch_config(batch, world=1, rank=0):
@@ -176,6 +208,7 @@ def algorithmic_bytes_kernel_a(cfg, win_bytes):
 
 
 FLUSH_BYTES = 256 << 20   # > 126 MB of L2
+STEADY_STATE_CYCLES = 12   # control cycles run before anything is timed or captured (converged control sequence)
 
 
 def time_resident(opt, steps, warmup, flush, stream):
@@ -209,7 +242,11 @@ def time_resident_python(opt, steps, warmup, flush, stream):
 def run_reference(args):
     """The reference's own CPU implementation of the path cannot be built here (no ROS 2 / Eigen);
     this arm times the oracle port (oracle/, -O3 -mavx2 -mfma, the reference's flags) on the host
-    cores.  The reference control path is single-threaded, so is this."""
+    cores.  The reference control path is single-threaded, so is this.  One "step" of this arm is a
+    bounded SAMPLE of the workload: as many back-to-back evalControl cycles as fit in ~0.25 s
+    (calibrated once), so a short --steps run still times seconds of CPU work, not milliseconds.
+    Nothing here maps the product library (navigation2_b200.params builds the configuration through
+    the host-only libmppi_config.so)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -223,26 +260,28 @@ def run_reference(args):
                                    holonomic=wl["holo"])
     o.setNoise(nvx, nvy, nwz)
     units = int(cfg.batch_size) * int(cfg.time_steps) * int(cfg.iteration_count)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         o.evalControl(wl["inp"])
-    times = []
-    n_ref = min(args.steps, 6000)  # ~2 ms each: bounded to ~12 s of CPU work
-    for _ in range(n_ref):
+    one = o.timeOptimize(wl["inp"], 5)                        # seconds per cycle
+    per_step = int(min(max(round(0.25 / max(one, 1e-6)), 1), 1000))
+    n_steps = min(args.steps, 400)                            # bounded: <= ~100 s of CPU work
+    singles = []
+    for _ in range(min(50, max(10, per_step))):                # single-call latencies for the p50
         t0 = time.perf_counter()
         o.evalControl(wl["inp"])
-        times.append(time.perf_counter() - t0)
-    times = np.array(times)
+        singles.append(time.perf_counter() - t0)
+    times = np.array([o.timeOptimize(wl["inp"], per_step) * per_step for _ in range(n_steps)])   # seconds per sample
     total = float(times.sum())
-    value = units * n_ref / total
+    value = units * per_step * n_steps / total
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n_ref,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / n_ref, "p50_ms": float(np.median(times) * 1e3),
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n_steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / n_steps, "cycles_per_step": per_step,
+        "ms_per_optimize": 1e3 * total / (n_steps * per_step), "p50_ms": float(np.median(singles) * 1e3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "batch_size": int(cfg.batch_size), "time_steps": int(cfg.time_steps),
-                   "iteration_count": int(cfg.iteration_count)},
+        "config": bench_config(wl, cfg),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{n_ref} full evalControl cycles of the workload (oracle port, g++ -O3 -mavx2 -mfma, 1 thread; "
-                                   "the reference's Eigen build needs ROS 2 and cannot be compiled here)"},
+                         "sample": f"{n_steps} samples of {per_step} back-to-back evalControl cycles of the workload (oracle port, "
+                                   "g++ -O3 -mavx2 -mfma, 1 thread; the reference's Eigen build needs ROS 2 and cannot be compiled here)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cpu": cpu_model(), "host_cores": os.cpu_count(),
     }
@@ -304,9 +343,11 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     flush = True  # L2 flushed before every timed step (mppi_time_resident, FLUSH_BYTES)
 
-    # first call through the public API: uploads the cycle inputs that the resident path replays
-    opt.evalControl(inputs)
-    opt.reset()
+    # Cycles through the public API until the control sequence has converged (the robot stands still, the sequence
+    # settles on driving along the path), then one more whose inputs the resident path replays: `value` times a
+    # steady-state optimize(), like the reference arm's closed loop, not the first cycle from a zero sequence.
+    for _ in range(STEADY_STATE_CYCLES):
+        opt.evalControl(inputs)
     opt.setResidentCapture(True)
     opt.evalControl(inputs)
 
@@ -348,7 +389,6 @@ def run_ours(args):
     # cycle inputs, ONE H2D copy, ONE kernel, result in mapped pinned memory, host sync.  Also reported: the
     # two-call sequence (mppi_upload_costmap stages the whole map first) and the same loop through Python. ----
     opt.setResidentCapture(False)
-    opt.reset()
 
     def timed_e2e(in_place):
         opt.timeE2E(wl["cells"], wl["resolution"], wl["origin"], inputs, args.warmup, in_place=in_place)
@@ -403,9 +443,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "batch_size": B, "time_steps": T, "iteration_count": iters, "n_robots_per_gpu": R,
-                   "parallelism": "independent controller per GPU, no collective" if world > 1 else "single GPU",
-                   "l2": "flushed before every timed step: a 256 MiB buffer overwritten (mppi_time_resident)"},
+        "config": bench_config(wl, cfg), "n_robots_per_gpu": R,
+        "state": f"steady state: {STEADY_STATE_CYCLES} control cycles before the captured / timed ones",
         "p50_optimize_us": float(np.median(step_ms) * 1e3),
         "p50_optimize_us_hot_l2": float(np.median(hot_ms) * 1e3),
         "value_hot_l2": world * units_per_step / (float(np.mean(hot_ms)) * 1e-3),
@@ -422,15 +461,23 @@ def run_ours(args):
         "clocks": clocks,
     }
 
-    # single-GPU extras (rank 0 at N = 1 only): the HBM-regime kernels, the inflation pass, the CPU baseline
+    opt.shutdown()
+    # the two multi-GPU workloads of north_star, at every N (every rank takes part; rank 0 gets the numbers)
+    if not args.no_large_batch and args.workload == "c1":
+        c4 = section_c4_sharded(args, world, rank)
+        c5 = section_c5_fleet(args, world, rank, stream)
+        if rank == 0:
+            line["c4_sharded"] = c4
+            line["c5_fleet"] = c5
+    # single-GPU extras (rank 0 at N = 1 only): the HBM-regime kernels, the inflation pass, the reference harness, the CPU baseline
     if rank == 0 and world == 1 and not args.no_large_batch and args.workload == "c1":
         line["roofline_large_batch"] = large_batch_roofline(peak, peak_src, stream, flush)
         line["costmap_inflation"] = inflation_pass(wl, peak, peak_src)
+        line["reference_harness"] = reference_harness_section(stream, not args.no_cpu_baseline)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl)
     if rank == 0:
         emit(line)
-    opt.shutdown()
     if distributed:
         dist.destroy_process_group()
 
@@ -483,6 +530,8 @@ def large_batch_roofline(peak, peak_src, stream, flush):
     wl = workload_c1()
     cfg = large_batch_config(1 << 20)
     opt = setup_engine(wl, cfg=cfg)
+    for _ in range(STEADY_STATE_CYCLES):
+        opt.evalControl(wl["inp"])
     opt.setResidentCapture(True)
     opt.evalControl(wl["inp"])
     opt.setKernelTiming(True)
@@ -530,61 +579,275 @@ def cpu_baseline(wl):
     sec = o.timeOptimize(wl["inp"], cycles)
     units = B * int(cfg.time_steps) * int(cfg.iteration_count)
     o.shutdown()
-    return {"value": units / sec, "unit": UNIT, "cores": 1, "kind": "port", "ms_per_optimize": sec * 1e3,
-            "sample": f"{cycles} evalControl cycles of the same workload (~{cycles * sec:.0f} s), oracle/ C++ restatement, "
-                      "g++ -O3 -mavx2 -mfma, single thread like the reference's control path",
-            "host_cpu": cpu_model(), "host_cores": os.cpu_count()}
+    out = {"value": units / sec, "unit": UNIT, "cores": 1, "kind": "port", "ms_per_optimize": sec * 1e3,
+           "sample": f"{cycles} evalControl cycles of the same workload (~{cycles * sec:.0f} s), oracle/ C++ restatement, "
+                     "g++ -O3 -mavx2 -mfma, single thread like the reference's control path",
+           "host_cpu": cpu_model(), "host_cores": os.cpu_count()}
+    # Courtesy upper bound: every host core runs its own independent controller on the same
+    # workload (the reference has no intra-optimize() threading; a fleet of controllers is what more cores buy).
+    try:
+        n_thr = max(1, len(os.sched_getaffinity(0)))
+        per = max(3, int(4.0 / max(sec, 1e-6)))
+
+        def worker(res, i):
+            ow = OracleOptimizer(cfg, fast=True)
+            ow.setCostmap(wl["cells"], wl["resolution"], *wl["origin"])
+            ow.setNoise(nvx, nvy, nwz)
+            ow.timeOptimize(wl["inp"], 3)
+            res[i] = ow.timeOptimize(wl["inp"], per) * per      # the C call releases the GIL
+            ow.shutdown()
+
+        res = [0.0] * n_thr
+        threads = [threading.Thread(target=worker, args=(res, i)) for i in range(n_thr)]
+        t0 = time.perf_counter()
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        wall = max(max(res), 1e-9)
+        out["all_cores"] = {"value": units * per * n_thr / wall, "unit": UNIT, "cores": n_thr, "kind": "port",
+                            "sample": f"{n_thr} threads x {per} evalControl cycles, one independent controller per thread "
+                                      f"(wall {time.perf_counter() - t0:.1f} s incl. set-up)"}
+    except Exception as exc:
+        out["all_cores"] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
+
+
+def _parity_errors(g, c, g_costs, c_costs):
+    """Worst deviations of one GPU cycle from the oracle's: (control sequence abs, cmd_vel abs, cost relative)."""
+    u_err = float(np.max(np.abs(np.asarray(g.control_sequence, dtype=np.float64) - c.control_sequence)))
+    cmd_err = float(np.max(np.abs(np.array(g.cmd, dtype=np.float64) - np.array(c.cmd))))
+    gc, cc = np.asarray(g_costs, dtype=np.float64), np.asarray(c_costs, dtype=np.float64)
+    cost_err = float(np.max(np.abs(gc - cc) / np.maximum(np.abs(cc), 1e-6)))
+    return u_err, cmd_err, cost_err
+
+
+def section_c4_sharded(args, world, rank):
+    """BASELINE.json configs[3]: ONE 2^20 x 56 batch sharded along the trajectory axis over the ranks (strong scaling).
+    A cycle is one mppi_shard_cycle call per rank: cycle inputs H2D, four kernels per iteration with the two
+    exchanges (MAX of the reduction words, gather of the softmax slots) done inside them over peer memory, result
+    block read from mapped memory.  Timed inside the library around whole calls, max over ranks.  Before anything is
+    timed, the first cycle is checked against the CPU oracle fed the GPU's own Philox tensors (rank 0).
+    At N > 1 rank 0 also times the unsharded batch on its own GPU (`n1_ms`), so the line carries both ends of the
+    strong-scaling ratio from the same box and process."""
+    import torch
+    import torch.distributed as dist
+    from navigation2_b200 import capi
+    from navigation2_b200.sharded import ShardedOptimizer
+    out = {"workload": "C4 DiffDrive 1048576x56 (BASELINE.json configs[3]) sharded along the trajectory axis, Philox noise "
+                       "keyed by global trajectory id", "scaling": "strong", "n_gpus": world, "unit": UNIT}
+    try:
+        wl = workload_c1()
+        batch = 1 << 20
+        cfg = large_batch_config(batch, world=world, rank=rank)
+        opt = ShardedOptimizer(cfg)
+        opt.setCostmap(wl["cells"], wl["resolution"], *wl["origin"])
+        peer = bool(opt._peer_exchange)
+        units = batch * int(cfg.time_steps) * int(cfg.iteration_count)
+        one = cpu = None
+        if rank == 0:
+            from oracle.binding import OracleOptimizer
+            cfg1 = large_batch_config(batch)
+            one = opt if world == 1 else ShardedOptimizer(cfg1)      # unsharded: the global Philox tensors and the N = 1 time
+            if one is not opt:
+                one.setCostmap(wl["cells"], wl["resolution"], *wl["origin"])
+            cpu = OracleOptimizer(cfg1)
+            cpu.setNoise(*[one.getTensor(t) for t in (capi.TENSOR_NOISE_VX, capi.TENSOR_NOISE_VY, capi.TENSOR_NOISE_WZ)])
+            cpu.setCostmap(wl["cells"], wl["resolution"], *wl["origin"])
+        if world > 1:
+            dist.barrier()               # an exchange waits 2 s for its peers: start the cycle together
+        g = opt.evalControl(wl["inp"])
+        if rank == 0:
+            c = cpu.evalControl(wl["inp"])
+            lo = opt.getTensor(capi.TENSOR_COSTS)
+            u_err, cmd_err, cost_err = _parity_errors(g, c, lo, cpu.getTensor(capi.TENSOR_COSTS)[: lo.shape[0]])
+            out["parity_checked"] = bool(u_err <= 1e-5 and cmd_err <= 1e-5 and cost_err <= 1e-4)
+            out["parity"] = {"against": "CPU oracle, same Philox tensors, first cycle", "control_sequence_abs": u_err,
+                             "cmd_vel_abs": cmd_err, "cost_rel": cost_err, "tolerances": [1e-5, 1e-5, 1e-4]}
+            cpu.shutdown()
+        if world > 1:
+            dist.barrier()
+        for _ in range(STEADY_STATE_CYCLES):
+            opt.evalControl(wl["inp"])
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        n = int(min(max(args.steps, 20), 200))
+        l0 = opt.launchCount()
+        t = opt.timeCycles(wl["inp"], n)
+        torch.cuda.synchronize()
+        launches = opt.launchCount() - l0
+        total = torch.tensor([float(t.sum())], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        ms = float(total.item()) * 1e3 / n
+        out.update({"ms_per_cycle": ms, "value": units / (ms * 1e-3), "cycles_timed": n,
+                    "p50_ms_rank0": float(np.median(t) * 1e3),
+                    "exchange": ("peer" if peer else "nccl") if world > 1 else "none (one rank)",
+                    "gpu_launches_per_cycle": launches / n,
+                    "timed": "steady_clock around whole mppi_shard_cycle calls inside the library (host preparation, H2D of "
+                             "the cycle block, kernels + exchanges, result block), sum over cycles, max over ranks; "
+                             f"after {STEADY_STATE_CYCLES} warm-up cycles; working set 470 MB of noise / N per GPU"})
+        if rank == 0:
+            if one is opt:
+                out["n1_ms"] = ms
+            else:
+                for _ in range(STEADY_STATE_CYCLES + 1):
+                    one.evalControl(wl["inp"])
+                out["n1_ms"] = float(one.timeCycles(wl["inp"], 30).sum()) * 1e3 / 30
+                one.shutdown()
+            out["strong_scaling_speedup"] = out["n1_ms"] / ms
+        if world > 1:
+            dist.barrier()
+        opt.shutdown()
+    except Exception as exc:  # the headline line must still be printed
+        out["error"] = f"{type(exc).__name__}: {exc}"
+        out["parity_checked"] = False
+    return out
+
+
+def fleet_workload(n_robots, rank):
+    """BASELINE.json configs[4] for one GPU's robot-set: every robot its own 200x200 costmap (16 distinct seeded maps
+    cycled over the fleet, each robot its own array), its own pose heading and path."""
+    from navigation2_b200 import scenarios as S
+    import navigation2_b200 as nb
+    rng = np.random.default_rng(1000 + rank)
+    base = [S.block_costmap(200, 200, 0.05, seed=31 + 16 * rank + k, keep_clear=(5.0, 5.0), n_blocks=10) for k in range(16)]
+    maps, inputs = [], []
+    for r in range(n_robots):
+        maps.append((base[r % 16].copy(), 0.05, 0.0, 0.0))
+        yaw = float(rng.uniform(-3.1, 3.1))
+        path = S.arc_path((5.0, 5.0, yaw), n_points=100, curvature=float(rng.uniform(-0.25, 0.25)))
+        inputs.append(nb.CycleInput(pose=(5.0, 5.0, yaw), speed=(0.2, 0.0, 0.0), path=path, goal=tuple(path[-1]),
+                                    goal_checker_xy_tolerance=0.25))
+    return maps, inputs
+
+
+def section_c5_fleet(args, world, rank, stream):
+    """BASELINE.json configs[4]: a fleet of independent robots, 2000 x 56 each, one robot-set per GPU, no collective
+    (weak scaling).  device_value: resident replays of a steady-state fleet cycle, CUDA events, L2 flushed;
+    e2e_value: mppi_optimize_in_place with every robot's costmap and path in host memory.  Two robots of rank 0's
+    set are checked against their own CPU oracle first."""
+    import torch
+    import torch.distributed as dist
+    import navigation2_b200 as nb
+    from navigation2_b200 import capi, params as P
+    R = int(args.robots)
+    out = {"workload": f"C5 fleet (BASELINE.json configs[4]): {R} independent robots per GPU, own 200x200 costmap + path "
+                       "each, DiffDrive 2000x56", "scaling": "weak", "n_gpus": world, "robots_per_gpu": R, "unit": UNIT}
+    try:
+        cfg = P.nav2_bringup_config(n_robots=R)
+        cfg1 = P.nav2_bringup_config()
+        maps, inputs = fleet_workload(R, rank)
+        opt = nb.Optimizer(cfg)
+        units = R * int(cfg.batch_size) * int(cfg.time_steps) * int(cfg.iteration_count)
+        first = opt.evalControl(inputs, costmaps=maps)
+        if rank == 0:
+            from oracle.binding import OracleOptimizer
+            worst = [0.0, 0.0, 0.0]
+            for r in sorted({0, R - 1}):
+                cpu = OracleOptimizer(cfg1)
+                cpu.setNoise(*[opt.getTensor(t, r) for t in (capi.TENSOR_NOISE_VX, capi.TENSOR_NOISE_VY, capi.TENSOR_NOISE_WZ)])
+                cpu.setCostmap(*maps[r])
+                c = cpu.evalControl(inputs[r])
+                errs = _parity_errors(first[r], c, opt.getTensor(capi.TENSOR_COSTS, r), cpu.getTensor(capi.TENSOR_COSTS))
+                worst = [max(a, b) for a, b in zip(worst, errs)]
+                cpu.shutdown()
+            out["parity_checked"] = bool(worst[0] <= 1e-5 and worst[1] <= 1e-5 and worst[2] <= 1e-4)
+            out["parity"] = {"against": f"CPU oracle per robot (robots 0 and {R - 1}), same Philox tensors, first cycle",
+                             "control_sequence_abs": worst[0], "cmd_vel_abs": worst[1], "cost_rel": worst[2]}
+        for _ in range(STEADY_STATE_CYCLES):
+            opt.evalControl(inputs, costmaps=maps)
+        # device: stage the maps, capture a steady-state cycle, replay it resident
+        for r in range(R):
+            opt.setCostmap(*maps[r], robot=r)
+        opt.setResidentCapture(True)
+        opt.evalControl(inputs)
+        n_dev = int(min(max(args.steps, 10), 50))
+        l0 = opt.launchCount()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        dev_ms = time_resident(opt, n_dev, 3, True, stream)
+        launches = (opt.launchCount() - l0) * n_dev // (n_dev + 3)
+        opt.setResidentCapture(False)
+        n_e2e = int(min(max(args.steps, 10), 40))
+        opt.timeE2EViews(maps, inputs, 3)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        b0 = opt.h2dByteCount()
+        e2e_t = opt.timeE2EViews(maps, inputs, n_e2e)
+        h2d = (opt.h2dByteCount() - b0) / n_e2e
+        tot = torch.tensor([float(dev_ms.sum()) * 1e-3, float(e2e_t.sum())], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = float(tot[0].item()) / n_dev, float(tot[1].item()) / n_e2e
+        out.update({"device_ms_per_fleet_cycle": dev_s * 1e3, "device_value": world * units / dev_s,
+                    "e2e_ms_per_fleet_cycle": e2e_s * 1e3, "e2e_value": world * units / e2e_s,
+                    "h2d_bytes_per_cycle": int(h2d), "d2h_bytes_per_cycle": int(R * (48 + 6 * int(cfg.time_steps) * 4)),
+                    "gpu_launches": int(launches), "window_misses": int(opt.windowMissCount()),
+                    "timed": "device: mppi_time_resident (CUDA events, L2 flushed before every replay), max over ranks; e2e: "
+                             "steady_clock around mppi_optimize_in_place calls with per-robot host costmaps inside the library"})
+        opt.shutdown()
+    except Exception as exc:
+        out["error"] = f"{type(exc).__name__}: {exc}"
+        out["parity_checked"] = False
+    return out
+
+
+def reference_harness_section(stream, with_cpu):
+    """The reference's own benchmark configuration (benchmark/optimizer_benchmark.cpp:49-99: iteration_count 2, 40x40
+    fixture), timed the same three ways as the headline: device-resident, end to end, CPU oracle on one core."""
+    try:
+        wl = workload_reference_harness()
+        cfg = wl["cfg"]
+        opt = setup_engine(wl)
+        units = int(cfg.batch_size) * int(cfg.time_steps) * int(cfg.iteration_count)
+        for _ in range(STEADY_STATE_CYCLES):
+            opt.evalControl(wl["inp"])
+        opt.setResidentCapture(True)
+        opt.evalControl(wl["inp"])
+        dev_ms = time_resident(opt, 200, 5, True, stream)
+        opt.setResidentCapture(False)
+        opt.timeE2E(wl["cells"], wl["resolution"], wl["origin"], wl["inp"], 10, in_place=True)
+        e2e = opt.timeE2E(wl["cells"], wl["resolution"], wl["origin"], wl["inp"], 300, in_place=True)
+        out = {"workload": wl["name"], "unit": UNIT, "value": units / (float(np.mean(dev_ms)) * 1e-3),
+               "p50_optimize_us": float(np.median(dev_ms) * 1e3),
+               "e2e": {"value": units * len(e2e) / float(e2e.sum()), "p50_latency_us": float(np.median(e2e) * 1e6)}}
+        opt.shutdown()
+        if with_cpu:
+            from oracle.binding import OracleOptimizer
+            from navigation2_b200 import scenarios as S
+            o = OracleOptimizer(cfg, fast=True)
+            o.setCostmap(wl["cells"], wl["resolution"], *wl["origin"])
+            o.setNoise(*S.seeded_noise(int(cfg.batch_size), int(cfg.time_steps), (cfg.vx_std, cfg.vy_std, cfg.wz_std)))
+            o.timeOptimize(wl["inp"], 5)
+            sec = o.timeOptimize(wl["inp"], 500)
+            o.shutdown()
+            out["cpu_baseline"] = {"value": units / sec, "unit": UNIT, "cores": 1, "kind": "port", "ms_per_optimize": sec * 1e3,
+                                   "sample": "500 evalControl cycles, oracle port, 1 thread"}
+        return out
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 def run_c4(args, world, rank, local_rank):
-    """BASELINE.json configs[3]: 2^20 x 56 sharded along the trajectory axis; per iteration one MAX
-    all-reduce of the reduction words and one all-gather of (min, sum, weighted control sums)."""
-    import torch
+    """`--workload c4`: the sharded 2^20 x 56 batch as the headline line (development runs; the default line carries the
+    same numbers in its c4_sharded section)."""
     import torch.distributed as dist
-    from navigation2_b200.sharded import ShardedOptimizer
-    wl = workload_c1()
-    batch = 1 << 20
-    cfg = large_batch_config(batch, world=world, rank=rank)
-    opt = ShardedOptimizer(cfg)
-    opt.setCostmap(wl["cells"], wl["resolution"], *wl["origin"])
-    stream = torch.cuda.current_stream()
-    for _ in range(args.warmup):
-        opt.evalControl(wl["inp"])
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    peer = bool(getattr(opt, "_peer_exchange", False))
-    if peer:
-        # exchanges over peer memory: a cycle is one library call (no host round trip between its kernels), timed
-        # inside the library on every rank; the slowest rank's total counts
-        t = opt.timeCycles(wl["inp"], args.steps)
-        torch.cuda.synchronize()
-        ms = torch.tensor([float(t.sum()) * 1e3], device="cuda", dtype=torch.float64)
-    else:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(opt._stream):
-            e0.record()
-            for _ in range(args.steps):
-                opt.evalControl(wl["inp"])
-            e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
-    units = batch * int(cfg.time_steps) * int(cfg.iteration_count)
+    sec = section_c4_sharded(args, world, rank)
     if rank == 0:
+        if "error" in sec:
+            raise SystemExit("c4: " + sec["error"])
+        wl = workload_c1()
+        cfg = large_batch_config(1 << 20)
         emit({
-            "metric": METRIC, "value": units * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": sec["value"], "unit": UNIT, "n_gpus": world, "steps": sec["cycles_timed"],
+            "warmup": STEADY_STATE_CYCLES, "ms_per_step": sec["ms_per_cycle"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C4 DiffDrive 1048576x56 sharded along the trajectory axis, Philox noise keyed by global id",
-                       "parallelism": f"batch shard x{world}; per iteration one MAX exchange of 8 words and one gather of 170 floats, "
-                                      + ("done by a kernel over peer memory (NVLink, CUDA IPC mailboxes)" if peer else
-                                         "by torch.distributed (NCCL) between the kernels"),
-                       "l2": "inputs (470 MB of noise per GPU at N=1) larger than L2"},
-            "gpu_launches": int(opt.launchCount())})
-    opt.shutdown()
+            "config": bench_config(dict(wl, name=sec["workload"]), cfg), "c4_sharded": sec,
+            "gpu_launches": int(round(sec["gpu_launches_per_cycle"] * sec["cycles_timed"]))})
     if world > 1:
         dist.destroy_process_group()
 

@@ -412,6 +412,11 @@ int mppi_set_resident_capture(MppiHandle * h, int enabled);
 int mppi_time_e2e(
   MppiHandle * h, const uint8_t * cells, uint32_t size_x, uint32_t size_y, double resolution, double origin_x,
   double origin_y, const MppiCycleIn * in, MppiCycleOut * out, int cycles, int in_place, double * per_call_seconds);
+/* The same measurement with one costmap view per robot (a fleet whose robots each own a map): `cycles`
+ * mppi_optimize_in_place calls, each timed with steady_clock on the calling thread. */
+int mppi_time_e2e_views(
+  MppiHandle * h, const MppiCostmapView * costmaps, const MppiCycleIn * in, MppiCycleOut * out, int cycles,
+  double * per_call_seconds);
 /* Kernels launched by this handle since creation (bench.py "gpu_launches"). */
 uint64_t mppi_launch_count(const MppiHandle * h);
 /* CUDA-event time of the dominant (rollout+score) kernel, averaged since the last call with

@@ -36,6 +36,28 @@
 #define MPPI_PIO2_LO 5.3903029534e-15f
 #define MPPI_2_OVER_PI 6.3661977237e-01f
 
+/* The arithmetic of mppi_sincosf for an argument already known to satisfy |x| < 1e8 (the caller checks; the
+ * rollout kernel tests the heading once per step and takes mppi_sincosf itself in the rare other case). */
+MPPI_HD void mppi_sincosf_in_range(float xs, float * s_out, float * c_out)
+{
+  const float k = rintf(xs * MPPI_2_OVER_PI);
+  float r = fmaf(-k, MPPI_PIO2_HI, xs);
+  r = fmaf(-k, MPPI_PIO2_MID, r);
+  r = fmaf(-k, MPPI_PIO2_LO, r);
+  const int q = static_cast<int>(k) & 3;
+  const float z = r * r;
+  float ps = fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+  ps = fmaf(ps, z, -1.6666654611e-1f);
+  const float sn = fmaf(ps * z, r, r);
+  float pc = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+  pc = fmaf(pc, z, 4.166664568298827e-2f);
+  const float cs = fmaf(pc * z, z, fmaf(-0.5f, z, 1.0f));
+  const float a = (q & 1) ? cs : sn;
+  const float b = (q & 1) ? sn : cs;
+  *s_out = (q & 2) ? -a : a;
+  *c_out = ((q + 1) & 2) ? -b : b;
+}
+
 /* sin and cos of x, ~1 ulp for |x| < ~1e4, deterministic everywhere (NaN for non-finite). */
 MPPI_HD void mppi_sincosf(float x, float * s_out, float * c_out)
 {

@@ -1,6 +1,7 @@
 """Builds the in-tree native libraries.
 
   navigation2_b200/libmppi_b200.so   the product: CUDA kernels + C ABI (include/mppi_b200.h), sm_100a only
+  navigation2_b200/libmppi_config.so the ABI's host-only configuration helpers on their own (no CUDA)
   oracle/_build/*.so, oracle/_ref/   the CPU oracle (test infrastructure) via oracle/Makefile
 
 `python -m navigation2_b200.build` builds both; `__graft_entry__.build()` calls build_all().
@@ -63,6 +64,22 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CONFIG_LIB = os.path.join(ROOT, "navigation2_b200", "libmppi_config.so")
+
+
+def build_config(force: bool = False, verbose: bool = False) -> str:
+    """csrc/mppi_config.cpp on its own (plain C++, no CUDA): what `params` needs to describe a workload, so the
+    reference arm of bench.py and the oracle-only tests do not map the product library."""
+    src = os.path.join(CSRC, "mppi_config.cpp")
+    if not force and not _stale(CONFIG_LIB, [src, os.path.join(ROOT, "include", "mppi_b200.h")]):
+        return CONFIG_LIB
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), src, "-o", CONFIG_LIB]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True, cwd=ROOT)
+    return CONFIG_LIB
+
+
 HOST = os.path.join(ROOT, "navigation2_b200", "host")
 HOST_LIB = os.path.join(ROOT, "navigation2_b200", "libmppi_controller_b200.so")
 HOST_TEST = os.path.join(HOST, "test_host")
@@ -107,6 +124,7 @@ def build_all(force: bool = False, verbose: bool = False) -> None:
         fcntl.flock(lock, fcntl.LOCK_EX)
         try:
             build_product(force=force, verbose=verbose)
+            build_config(force=force, verbose=verbose)
             build_host(force=force, verbose=verbose)
             build_oracle(verbose=verbose)
         finally:

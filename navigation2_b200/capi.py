@@ -223,6 +223,8 @@ SYMBOLS = {
     "mppi_set_resident_capture": (C.c_int, [_P, C.c_int]),
     "mppi_time_e2e": (C.c_int, [_P, _U8, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double,
                                 C.POINTER(MppiCycleIn), C.POINTER(MppiCycleOut), C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "mppi_time_e2e_views": (C.c_int, [_P, C.POINTER(MppiCostmapView), C.POINTER(MppiCycleIn), C.POINTER(MppiCycleOut), C.c_int,
+                                      C.POINTER(C.c_double)]),
     "mppi_optimize_in_place": (C.c_int, [_P, C.POINTER(MppiCostmapView), C.POINTER(MppiCycleIn), C.POINTER(MppiCycleOut)]),
     "mppi_window_miss_count": (C.c_uint64, [_P]),
     "mppi_h2d_byte_count": (C.c_uint64, [_P]),
@@ -275,6 +277,35 @@ def load_library(path: str | None = None) -> C.CDLL:
         fn.argtypes = args
     if path is None:
         _LIB = lib
+    return lib
+
+
+CONFIG_SYMBOLS = [
+    "mppi_default_config", "mppi_default_critic_params", "mppi_critic_type_from_name", "mppi_critic_name",
+    "mppi_status_string", "mppi_sizeof_config", "mppi_sizeof_critic_params", "mppi_sizeof_cycle_in",
+    "mppi_sizeof_cycle_out", "mppi_sizeof_optimizer_state", "mppi_sizeof_costmap_view", "mppi_inflation_compute_cost",
+]
+_CONFIG_LIB = None
+
+
+def load_config_library() -> C.CDLL:
+    """The host-only configuration helpers of the C ABI (csrc/mppi_config.cpp: parameter defaults, critic names,
+    status strings, struct sizes), built on their own as libmppi_config.so without any CUDA code.  `params` builds
+    MppiConfig structures through it, so a process that only describes a workload — bench.py's reference arm, the
+    CPU oracle's tests — never maps the product library."""
+    global _CONFIG_LIB
+    if _CONFIG_LIB is not None:
+        return _CONFIG_LIB
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmppi_config.so")
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} is missing: build it with `python -m navigation2_b200.build`")
+    lib = C.CDLL(p)
+    for name in CONFIG_SYMBOLS:
+        res, args = SYMBOLS[name]
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _CONFIG_LIB = lib
     return lib
 
 

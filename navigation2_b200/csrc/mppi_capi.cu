@@ -140,9 +140,9 @@ struct MppiHandle
   std::vector<void *> peer_mailboxes;     // [world]; own entry = d_mailbox
   unsigned char ** d_peers = nullptr;     // the same pointers on the device
   int32_t * d_xerror = nullptr, * h_xerror = nullptr;
+  uint32_t * d_xstate = nullptr;          // device words: exchanges completed per kind [2] + kernel A's block ticket (KArgs::xch_state)
   bool peers_open = false;
   int shard_iteration = 0;                // iterations launched since mppi_shard_begin
-  uint32_t xseq[2] = {0, 0};              // exchanges performed per kind (sequence number = xseq + 1, parity = xseq & 1)
   bool shard_failed = false;              // an exchange timed out: the ranks are out of step for good, the handle is dead
   uint8_t * d_flush = nullptr;    // mppi_time_resident: the buffer overwritten to flush L2
   size_t flush_bytes = 0;
@@ -457,7 +457,7 @@ int allocate(MppiHandle * h)
   CU_CHECK(h, cudaMalloc(&h->d_obs_raw, R * B * sizeof(float)));
   CU_CHECK(h, cudaMalloc(&h->d_obs_rep, R * B * sizeof(float)));
   CU_CHECK(h, cudaMalloc(&h->d_last, R * 3 * B * sizeof(float)));
-  CU_CHECK(h, cudaMalloc(&h->d_pa, std::max<size_t>(1, R * 3 * h->n_pa * B) * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_pa, std::max<size_t>(4, R * B * static_cast<size_t>((3 * h->n_pa + 3) & ~3)) * sizeof(float)));
   CU_CHECK(h, cudaMalloc(&h->d_costs, R * B * sizeof(float)));
   CU_CHECK(h, cudaMalloc(&h->d_softmax, R * B * sizeof(float)));
   CU_CHECK(h, cudaMemset(h->d_costs, 0, R * B * sizeof(float)));
@@ -827,7 +827,7 @@ KArgs make_args(MppiHandle * h)
   a.B = h->B; a.T = h->T; a.R = h->R;
   a.b_offset = static_cast<int>(h->cfg.shard_rank) * h->B;
   a.n_terms = static_cast<int>(h->cfg.n_critics) + 3;
-  a.n_pa = h->n_pa; a.pa_step = h->pa_step;
+  a.n_pa = h->n_pa; a.pa_step = h->pa_step; a.pa_stride = (3 * h->n_pa + 3) & ~3;
   a.max_path = h->max_path;
   a.world = static_cast<int>(h->cfg.shard_world); a.rank = static_cast<int>(h->cfg.shard_rank);
   a.n_partial_blocks = h->n_partial_blocks;
@@ -846,6 +846,15 @@ KArgs make_args(MppiHandle * h)
   a.dbg_cost_cells = h->d_dbg_cost; a.dbg_obstacle_cells = h->d_dbg_obs;
   a.red = h->d_red; a.partials = h->d_partials;
   a.ar2_slot = h->d_slot; a.ar2_all = h->cfg.shard_world == 1 ? h->d_slot : h->d_slot_all;
+  if (h->peers_open && h->cfg.shard_world > 1) {
+    a.xch_peers = h->d_peers;
+    a.xch_state = h->d_xstate;
+    a.xch_error = h->d_xerror;
+    a.xch_words_base = static_cast<uint32_t>(h->mailbox_words_base);
+    a.xch_words_stride = static_cast<uint32_t>(h->mailbox_words_stride);
+    a.xch_slots_base = static_cast<uint32_t>(h->mailbox_slots_base);
+    a.xch_slots_stride = static_cast<uint32_t>(h->mailbox_slots_stride);
+  }
   a.costmap = h->d_map; a.map_stride = h->map_stride;
   a.win_packets = h->d_packets; a.map_resident = 1;
   a.stamp_results = 0;
@@ -921,6 +930,15 @@ LaunchPlan make_plan(MppiHandle * h)
   const int kc = h->critic_of_type[MPPI_CRITIC_COST], kp = h->critic_of_type[MPPI_CRITIC_PATH_ALIGN];
   p.ka.cc_step = kc >= 0 ? static_cast<int>(h->cfg.critics[kc].trajectory_point_step) : 2;
   p.ka.pa_step = kp >= 0 ? static_cast<int>(h->cfg.critics[kp].trajectory_point_step) : 4;
+  p.ka.model = h->cfg.motion_model;
+  {
+    bool ok = !(kc >= 0 && h->cfg.critics[kc].consider_footprint) && !(kp >= 0 && h->cfg.critics[kp].use_path_orientations);
+    for (int r = 0; r < h->R && ok; ++r) {
+      const float res = static_cast<float>(h->robots[r].resolution);
+      ok = res >= 0x1p-60f && res <= 0x1p60f;
+    }
+    p.ka.lean_ok = ok;
+  }
   // fused path: the whole batch of a robot fits one thread-block cluster and nothing asks for the
   // full-feature kernels (tensor materialisation, debug dumps, visualisation, clamp_raw, input delay)
   p.fused = false;
@@ -1020,7 +1038,7 @@ int enqueue_iterations(
     }
     CU_CHECK(h, mppi_launch_softmax_partial(a, h->holo, stream));
     if (h->timing) {CU_CHECK(h, cudaEventRecord(c1, stream));}
-    CU_CHECK(h, mppi_launch_finalize(a, h->holo, 0, stream));
+    CU_CHECK(h, mppi_launch_finalize(a, h->holo, a.xch_peers ? 3 : 0, stream));
     h->launches += 4;
   }
   return MPPI_OK;
@@ -1041,7 +1059,9 @@ uint64_t plan_key(const MppiHandle * h, const LaunchPlan & p)
   mix(p.sm_a.total); mix(p.sm_a.path_cap); mix(p.sm_a.noise_stages); mix(p.sm_a.off_win); mix(p.sm_a.off_ring);
   mix(p.block_a); mix(p.block_b); mix(p.path_cap);
   mix(p.ka.block); mix(p.ka.holo); mix(p.ka.full); mix(p.ka.crit_types); mix(p.ka.cc_step); mix(p.ka.pa_step);
+  mix(p.ka.model); mix(p.ka.lean_ok); mix(p.sm_a.off_cc_lut);
   mix(h->cycle_block_bytes); mix(h->max_path); mix(h->map_stride); mix(h->cfg.visualize); mix(h->single_copy); mix(h->noise_flip); mix(h->poll_results);
+  mix(h->peers_open); mix(reinterpret_cast<uint64_t>(h->d_peers));
   return k;
 }
 
@@ -1309,6 +1329,7 @@ int mppi_destroy(MppiHandle * h)
   }
   if (h->d_mailbox) {cudaFree(h->d_mailbox);}
   if (h->d_peers) {cudaFree(h->d_peers);}
+  if (h->d_xstate) {cudaFree(h->d_xstate);}
   if (h->h_xerror) {cudaFreeHost(h->h_xerror);}
   if (h->d_flush) {cudaFree(h->d_flush);}
   for (auto & rb : h->robots) {if (rb.stage_event) {cudaEventDestroy(rb.stage_event);}}
@@ -1510,8 +1531,9 @@ namespace
 {
 int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycleIn * in, MppiCycleOut * out)
 {
-  if (h->cfg.shard_world != 1) {
-    h->error = "mppi_optimize on a sharded handle: use the mppi_shard_* phases";
+  if (h->cfg.shard_world != 1 && !h->peers_open) {
+    h->error = "mppi_optimize on a sharded handle without open peer mailboxes: use mppi_shard_open_peers + mppi_shard_cycle, "
+      "or the mppi_shard_* phases with collectives in between";
     return MPPI_ERR_UNSUPPORTED;
   }
   int max_n = 1;
@@ -1623,7 +1645,9 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
         CU_CHECK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         // single-launch plans: the cycle block already went up with the map (upload_arena); a copy node inside the
         // graph costs ~11 us of latency (measured), a stream-ordered copy ahead of a kernel-only graph ~5 us
-        int crc = single_copy ? MPPI_OK : upload_cycle_block(h, h->stream);
+        // The cycle block goes up with a stream-ordered copy AHEAD of a kernel-only graph (below), never as a copy node
+        // inside it: a copy node costs ~11 us of latency, a stream-ordered copy ~5 us (measured, tools/experiments).
+        int crc = MPPI_OK;
         if (crc == MPPI_OK && h->cfg.visualize && !plan.fused) {
           if (cudaMemsetAsync(h->d_collisions, 0, static_cast<size_t>(h->B) * h->R, h->stream) != cudaSuccess) {crc = MPPI_ERR_CUDA;}
           if (h->d_critic_costs &&
@@ -1654,6 +1678,10 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
         }
         if (h->graphs.size() >= 16) {drop_graphs(h);}
         h->graphs.push_back({key, exec});
+      }
+      if (!single_copy) {
+        rc = upload_cycle_block(h, h->stream);
+        if (rc != MPPI_OK) {return rc;}
       }
       CU_CHECK(h, cudaGraphLaunch(exec, h->stream));
       h->launches += static_cast<uint64_t>(h->cfg.iteration_count) * (plan.fused ? 1 : 4);
@@ -1790,6 +1818,21 @@ int mppi_time_e2e(
     if (rc != MPPI_OK) {return rc;}
     const auto t1 = std::chrono::steady_clock::now();
     per_call_seconds[i] = std::chrono::duration<double>(t1 - t0).count();
+  }
+  return MPPI_OK;
+}
+
+// The same with one costmap view per robot (fleets whose robots each own a map), always in place.
+int mppi_time_e2e_views(
+  MppiHandle * h, const MppiCostmapView * costmaps, const MppiCycleIn * in, MppiCycleOut * out, int cycles,
+  double * per_call_seconds)
+{
+  if (!h || !costmaps || !in || !out || !per_call_seconds || cycles < 1) {return MPPI_ERR_INVALID_ARGUMENT;}
+  for (int i = 0; i < cycles; ++i) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = mppi_optimize_in_place(h, costmaps, in, out);
+    if (rc != MPPI_OK) {return rc;}
+    per_call_seconds[i] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
   return MPPI_OK;
 }
@@ -2177,6 +2220,8 @@ int ensure_mailbox(MppiHandle * h)
   CU_CHECK(h, cudaMalloc(&h->d_mailbox, h->mailbox_bytes));
   CU_CHECK(h, cudaMemset(h->d_mailbox, 0, h->mailbox_bytes));
   CU_CHECK(h, cudaMalloc(&h->d_peers, sizeof(unsigned char *) * world));
+  CU_CHECK(h, cudaMalloc(&h->d_xstate, sizeof(uint32_t) * 4));
+  CU_CHECK(h, cudaMemset(h->d_xstate, 0, sizeof(uint32_t) * 4));
   // the timeout flag lives in mapped pinned memory: the host reads it after the cycle without another copy
   CU_CHECK(h, cudaHostAlloc(&h->h_xerror, sizeof(int32_t), cudaHostAllocMapped));
   *h->h_xerror = 0;
@@ -2184,33 +2229,6 @@ int ensure_mailbox(MppiHandle * h)
   return MPPI_OK;
 }
 
-int enqueue_exchange(MppiHandle * h, int kind)
-{
-  if (h->cfg.shard_world == 1) {return MPPI_OK;}  // nothing to exchange (make_args: the gathered slots ARE this rank's slot)
-  ShardExchangeArgs x{};
-  x.peers = h->d_peers;
-  x.world = static_cast<int32_t>(h->cfg.shard_world); x.rank = static_cast<int32_t>(h->cfg.shard_rank);
-  x.kind = kind;
-  // each kind has its own sequence counter and its own pair of payload buffers: exchange n + 1 of a kind writes the
-  // buffer exchange n did not use, and a rank can only start n + 2 after every peer has published n + 1, i.e. after
-  // every peer has finished reading n — whatever the order in which the two kinds are called
-  x.parity = static_cast<int32_t>(h->xseq[kind] & 1u);
-  x.seq = h->xseq[kind] + 1u;
-  x.payload_base = kind == 0 ? h->mailbox_words_base : h->mailbox_slots_base;
-  x.payload_stride = kind == 0 ? h->mailbox_words_stride : h->mailbox_slots_stride;
-  x.n_words = kind == 0 ? RED_WORDS * h->R : (2 + 3 * h->T) * h->R;
-  if (static_cast<size_t>(x.n_words) * 4u > x.payload_stride) {
-    h->error = "exchange payload larger than the mailbox slot (time_steps changed on a live sharded handle?)";
-    return MPPI_ERR_INVALID_ARGUMENT;
-  }
-  x.src = reinterpret_cast<const uint32_t *>(kind == 0 ? static_cast<void *>(h->d_red) : static_cast<void *>(h->d_slot));
-  x.dst = reinterpret_cast<uint32_t *>(kind == 0 ? static_cast<void *>(h->d_red) : static_cast<void *>(h->d_slot_all));
-  x.error = h->d_xerror;
-  CU_CHECK(h, mppi_launch_shard_exchange(x, h->stream));
-  h->xseq[kind]++;
-  h->launches++;
-  return MPPI_OK;
-}
 }  // namespace
 
 int mppi_shard_ipc_handle(MppiHandle * h, unsigned char * handle64)
@@ -2240,6 +2258,7 @@ int mppi_shard_open_peers(MppiHandle * h, const unsigned char * handles)
   }
   CU_CHECK(h, cudaMemcpy(h->d_peers, h->peer_mailboxes.data(), sizeof(void *) * world, cudaMemcpyHostToDevice));
   h->peers_open = true;
+  drop_graphs(h);
   return MPPI_OK;
 }
 
@@ -2265,6 +2284,7 @@ int mppi_shard_rollout(MppiHandle * h)
   if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
   const LaunchPlan plan = make_plan(h);
   KArgs a = make_args(h);
+  a.xch_peers = nullptr;  // the caller runs the collectives between the phases
   CU_CHECK(h, mppi_launch_rollout_score(a, plan.sm_a, plan.ka, h->stream));
   h->launches += 1;
   return MPPI_OK;
@@ -2275,6 +2295,7 @@ int mppi_shard_score(MppiHandle * h)
   if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
   const LaunchPlan plan = make_plan(h);
   KArgs a = make_args(h);
+  a.xch_peers = nullptr;
   a.zero_costs = h->shard_iteration == 0 ? 1 : 0;
   CU_CHECK(h, mppi_launch_path_score(a, plan.path_cap, h->holo, false, plan.block_b, h->stream));
   CU_CHECK(h, mppi_launch_softmax_partial(a, h->holo, h->stream));
@@ -2287,6 +2308,7 @@ int mppi_shard_update(MppiHandle * h, int last_iteration)
 {
   if (check_handle(h) != MPPI_OK) {return MPPI_ERR_INVALID_ARGUMENT;}
   KArgs a = make_args(h);
+  a.xch_peers = nullptr;
   a.last_iteration = last_iteration ? 1 : 0;
   CU_CHECK(h, mppi_launch_finalize(a, h->holo, 2, h->stream));
   h->launches += 1;
@@ -2295,7 +2317,8 @@ int mppi_shard_update(MppiHandle * h, int last_iteration)
 }
 
 // A whole sharded evalControl with the two exchanges done on the device over peer memory: every rank calls it with
-// the same inputs; nothing between the kernels of an iteration goes through the host.
+// the same inputs.  It is mppi_optimize's own cycle (same host state machine, same captured graph of four kernels per
+// iteration, result block polled in mapped memory); the exchanges are folded into kernels A / B / D (KArgs::xch_*).
 int mppi_shard_cycle(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
 {
   if (!h || !in || !out) {return MPPI_ERR_INVALID_ARGUMENT;}
@@ -2304,33 +2327,8 @@ int mppi_shard_cycle(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
     h->error = "an earlier exchange timed out: the ranks are out of step, destroy and re-create the sharded handles";
     return MPPI_ERR_CUDA;
   }
-  const auto ht0 = std::chrono::steady_clock::now();
-  int rc = mppi_shard_begin(h, in);
-  if (rc != MPPI_OK) {return rc;}
-  const auto ht1 = std::chrono::steady_clock::now();
-  const int iters = static_cast<int>(h->cfg.iteration_count);
-  while (true) {
-    for (int it = 0; it < iters; ++it) {
-      rc = mppi_shard_rollout(h);
-      if (rc == MPPI_OK) {rc = enqueue_exchange(h, 0);}
-      if (rc == MPPI_OK) {rc = mppi_shard_score(h);}
-      if (rc == MPPI_OK) {rc = enqueue_exchange(h, 1);}
-      if (rc == MPPI_OK) {rc = mppi_shard_update(h, it == iters - 1 ? 1 : 0);}
-      if (rc != MPPI_OK) {return rc;}
-    }
-    const auto ht2 = std::chrono::steady_clock::now();
-    rc = mppi_shard_end(h, out);
-    if (h->host_timers) {
-      const auto ht3 = std::chrono::steady_clock::now();
-      h->ht[1] += std::chrono::duration<double>(ht1 - ht0).count();
-      h->ht[3] += std::chrono::duration<double>(ht2 - ht1).count();
-      h->ht[4] += std::chrono::duration<double>(ht3 - ht2).count();
-      h->ht_n++;
-    }
-    if (rc == 1) {continue;}  // fallback(): every rank saw the same flags and retries together
-    if (rc != MPPI_OK) {return rc;}
-    break;
-  }
+  if (h->R != 1 && h->cfg.shard_world > 1) {h->error = "batch sharding drives one robot per handle"; return MPPI_ERR_UNSUPPORTED;}
+  const int rc = optimize_impl(h, nullptr, in, out);
   if (h->h_xerror && *static_cast<volatile int32_t *>(h->h_xerror)) {
     // The kernels after a timed-out exchange ran on stale payloads and committed their result on this rank, and the
     // peers are one exchange out of step: nothing on this handle can be trusted any more.  It is marked dead (every
@@ -2340,7 +2338,7 @@ int mppi_shard_cycle(MppiHandle * h, const MppiCycleIn * in, MppiCycleOut * out)
     h->error = "a peer did not reach an exchange within 2 s; the sharded handle is dead, re-create it on every rank";
     return MPPI_ERR_CUDA;
   }
-  return MPPI_OK;
+  return rc;
 }
 
 // `cycles` back-to-back mppi_shard_cycle calls, each timed with steady_clock on the calling thread (all ranks call it)

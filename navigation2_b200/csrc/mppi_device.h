@@ -151,6 +151,7 @@ struct KArgs
   int32_t n_terms;      // n_critics + 3 gamma slots
   int32_t n_pa;         // PathAlign strided samples per trajectory
   int32_t pa_step;
+  int32_t pa_stride;    // floats per trajectory row of pa_samples: 3 * n_pa rounded up to a multiple of 4
   int32_t max_path;     // stride of the path arrays
   int32_t world;        // shard world size
   int32_t rank;
@@ -174,7 +175,8 @@ struct KArgs
   float * obs_raw;      // [R][B]
   float * obs_rep;      // [R][B]
   float * last_xyz;     // [R][3][B]
-  float * pa_samples;   // [R][3][n_pa][B]
+  float * pa_samples;   // [R][B][pa_stride]: per trajectory x0 y0 x1 y1 ... then yaw0 yaw1 ... (a thread's row is contiguous:
+                        // kernel A stores with immediate offsets, kernel B fetches it with 16-byte loads)
   float * costs;        // [R][B] running total (accumulates over iterations)
   float * softmax;      // [R][B]
   float * critic_costs; // [R][n_critics][B] or null (visualize)
@@ -185,6 +187,16 @@ struct KArgs
   float * partials;     // [R][n_partial_blocks][1 + 3T]
   float * ar2_slot;     // [R][2 + 3T] this rank's (min, sum, W)
   const float * ar2_all;// [world][R][2 + 3T]
+  // Batch sharding with both exchanges folded into the kernels (peer memory over NVLink, one robot): the last block of
+  // kernel A pushes the reduction words into every rank's mailbox, every block of kernel B waits for its peers' words and
+  // reduces them, the finalize kernel pushes this rank's softmax slot, waits and combines.  xch_peers == nullptr: no
+  // folded exchange (single GPU, or the caller runs collectives between the mppi_shard_* phases).
+  // Mailbox layout, identical on every rank: uint32 seq[2 kinds][2 parities][world], then per kind a payload area
+  // [2 parities][world][stride bytes].  Exchange number n of a kind uses parity n & 1 and publishes n + 1.
+  unsigned char * const * xch_peers;   // [world] mailbox base pointers (peers' opened with CUDA IPC)
+  uint32_t * xch_state;                // device words: [0] / [1] exchanges of kind 0 / 1 completed, [2] kernel A blocks done
+  int32_t * xch_error;                 // mapped host word, set when a peer did not show up within the timeout
+  uint32_t xch_words_base, xch_words_stride, xch_slots_base, xch_slots_stride;  // bytes
   const uint8_t * costmap;  // [R][map_stride]
   size_t map_stride;
   // Single-launch cycles upload only the window of the costmap the trajectories can plausibly reach, packed

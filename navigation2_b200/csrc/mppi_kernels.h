@@ -13,6 +13,7 @@ struct KSmemA
   uint32_t off_u;      // float u[3][T]
   uint32_t off_path;   // float path x / y / integrated distance, path_cap each
   uint32_t off_lut;    // float obstacle distance LUT [2][256]
+  uint32_t off_cc_lut; // float CostCritic score per cell cost [256] (k_rollout_lean)
   uint32_t off_ring;   // float delay ring [3][ring_depth][block]
   uint32_t off_win;    // uint8 costmap window
   uint32_t off_noise;  // float noise ring [noise_stages][axes][MPPI_TCHUNK_A][block], filled by cp.async.bulk
@@ -25,6 +26,7 @@ struct KSmemA
 struct KSmemB
 {
   int32_t path_cap;
+  uint32_t off_pa;     // float [pa_stride][block]: the block's PathAlign sample rows, transposed
   uint32_t total;
 };
 
@@ -61,6 +63,9 @@ struct KPlanA
   bool full;             // materialize / debug cells / collision flags / clamp_raw_controls / input delay
   uint32_t crit_types;   // union of CRIT bits (1 << MppiCriticType) of the critics active this call
   int cc_step, pa_step;  // trajectory_point_step of CostCritic / PathAlignCritic (0 if absent)
+  int model;             // MppiMotionModel
+  bool lean_ok;          // nothing in the configuration rules out k_rollout_lean (point collision checks in CostCritic,
+                         // no path orientations in PathAlign, costmap resolution inside exact_div's range)
 };
 
 cudaError_t mppi_launch_rollout_score(
@@ -68,7 +73,8 @@ cudaError_t mppi_launch_rollout_score(
 cudaError_t mppi_launch_path_score(
   const KArgs & a, int path_cap, bool holo, bool from_tensors, int block, cudaStream_t stream);
 cudaError_t mppi_launch_softmax_partial(const KArgs & a, bool holo, cudaStream_t stream);
-// shard_stage: 0 single GPU, 1 reduce partials into this rank's slot, 2 combine slots + finalize
+// shard_stage: 0 single GPU, 1 reduce partials into this rank's slot, 2 combine slots + finalize,
+// 3 reduce + exchange over peer memory (KArgs::xch_*) + combine + finalize in one launch
 cudaError_t mppi_launch_finalize(const KArgs & a, bool holo, int shard_stage, cudaStream_t stream);
 cudaError_t mppi_launch_philox(
   float * nvx, float * nvy, float * nwz, int B, int T, int R, int b_offset, uint64_t seed,
@@ -76,23 +82,5 @@ cudaError_t mppi_launch_philox(
 
 cudaError_t mppi_launch_selftest_exact_math(
   const float * a, const float * b, int n, unsigned int * mismatches, unsigned int * flagged, cudaStream_t stream);
-
-// One exchange of a sharded iteration over peer memory (k_shard_exchange).  Mailbox layout, identical on every rank:
-// uint32 seq[2 kinds][2 parities][world], then per kind a payload area [2 parities][world][payload_stride bytes].
-struct ShardExchangeArgs
-{
-  unsigned char * const * peers;   // device array of `world` mailbox base pointers (peers' opened with CUDA IPC)
-  int32_t world, rank;
-  int32_t kind;                    // 0: reduction words (MAX-reduced into dst), 1: softmax slots (gathered into dst)
-  int32_t parity;
-  uint32_t seq;
-  size_t payload_base;             // byte offset of this kind's payload area
-  size_t payload_stride;           // bytes per rank slot
-  int32_t n_words;                 // 4-byte words in one payload
-  const uint32_t * src;            // this rank's payload (device)
-  uint32_t * dst;                  // n_words (kind 0) or world * n_words (kind 1) words
-  int32_t * error;                 // set to 1 when a peer did not show up within the timeout
-};
-cudaError_t mppi_launch_shard_exchange(const ShardExchangeArgs & x, cudaStream_t stream);
 
 #endif  // NAVIGATION2_B200_CSRC_MPPI_KERNELS_H_

@@ -324,6 +324,26 @@ class Optimizer(EngineBase):
         _raise_for(self._lib, self._h, rc)
         return t
 
+    def timeE2EViews(self, costmaps, inputs, cycles: int) -> np.ndarray:
+        """Per-call seconds of `cycles` mppi_optimize_in_place calls with one (cells, resolution, origin_x, origin_y) per
+        robot, timed inside the C library."""
+        ins = [inputs] if isinstance(inputs, CycleInput) else list(inputs)
+        maps = [costmaps] if isinstance(costmaps, tuple) else list(costmaps)
+        if len(ins) != self.R or len(maps) != self.R:
+            raise ValueError(f"expected {self.R} inputs and costmaps")
+        c_in = (capi.MppiCycleIn * self.R)(*[i.to_c() for i in ins])
+        c_out = (capi.MppiCycleOut * self.R)()
+        keep = [np.ascontiguousarray(m[0], dtype=np.uint8) for m in maps]
+        views = (capi.MppiCostmapView * self.R)()
+        for r, (m, cells) in enumerate(zip(maps, keep)):
+            views[r].cells = cells.ctypes.data_as(C.POINTER(C.c_uint8))
+            views[r].size_x, views[r].size_y = cells.shape[1], cells.shape[0]
+            views[r].resolution, views[r].origin_x, views[r].origin_y = float(m[1]), float(m[2]), float(m[3])
+        t = np.zeros(cycles, dtype=np.float64)
+        rc = self._lib.mppi_time_e2e_views(self._h, views, c_in, c_out, int(cycles), t.ctypes.data_as(C.POINTER(C.c_double)))
+        _raise_for(self._lib, self._h, rc)
+        return t
+
     def enqueueResident(self, cuda_stream: int | None = None) -> None:
         _raise_for(self._lib, self._h, self._lib.mppi_enqueue_resident(self._h, cuda_stream))
 

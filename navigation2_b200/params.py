@@ -62,7 +62,7 @@ NAV2_BRINGUP_COSTMAP = {"robot_radius": 0.22, "cost_scaling_factor": 3.0, "infla
 
 def critic_params(name: str, overrides: Mapping[str, Any] | None = None) -> capi.MppiCriticParams:
     """Code defaults of mppi::critics::<name> with `<name>.<param>` overrides applied."""
-    lib = capi.load_library()
+    lib = capi.load_config_library()
     short = name.split("::")[-1]
     ctype = lib.mppi_critic_type_from_name(short.encode())
     if ctype < 0:
@@ -137,7 +137,7 @@ def make_config(
     inflation         {"cost_scaling_factor", "inflation_radius"} of the costmap's inflation layer, or None
     validator         TrajectoryValidator.{enabled, collision_lookahead_time, consider_footprint}
     """
-    lib = capi.load_library()
+    lib = capi.load_config_library()
     cfg = capi.MppiConfig()
     rc = lib.mppi_default_config(cfg)
     if rc != capi.MPPI_OK:

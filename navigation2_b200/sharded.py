@@ -41,17 +41,11 @@ class ShardedOptimizer(Optimizer):
         self._distributed = self.world > 1
         if self._distributed and (not dist.is_initialized() or dist.get_world_size(group) != self.world):
             raise RuntimeError("shard_world does not match the torch.distributed world size")
-        # Kernels and torch.distributed collectives must be ordered on ONE stream.  The legacy default stream has
-        # handle 0, which mppi_set_stream reads as "the handle's own stream": kernels and collectives would then run
-        # unordered (ranks diverge).  So a dedicated torch stream is used unless the caller already made one current.
-        cur = torch.cuda.current_stream()
-        self._stream = cur if cur.cuda_stream != 0 else torch.cuda.Stream()
-        _raise_for(self._lib, self._h, self._lib.mppi_set_stream(self._h, self._stream.cuda_stream))
-        self._bind_exchange_buffers()
-        # Exchanges over peer memory (k_shard_exchange): every rank exports its mailbox as a CUDA IPC handle, the
-        # handles are all-gathered once, and from then on a cycle never goes through the host between its kernels.
-        # MPPI_B200_NCCL_EXCHANGE=1 keeps the torch.distributed collectives between the kernels (A/B measurements).
-        self._peer_exchange = not self._distributed   # one rank: mppi_shard_cycle has nothing to exchange
+        # Exchanges over peer memory (folded into the kernels, KArgs::xch_*): every rank exports its mailbox as a CUDA IPC
+        # handle, the handles are all-gathered once, and from then on a cycle is mppi_optimize's own captured graph of
+        # four kernels per iteration on the handle's own stream.  MPPI_B200_NCCL_EXCHANGE=1 (or a non-NCCL backend)
+        # keeps torch.distributed collectives between the mppi_shard_* phases instead (A/B measurements).
+        self._peer_exchange = not self._distributed   # one rank: nothing to exchange
         if self._distributed and os.environ.get("MPPI_B200_NCCL_EXCHANGE", "0") != "1" and dist.get_backend(group) == "nccl":
             mine = (C.c_ubyte * 64)()
             _raise_for(self._lib, self._h, self._lib.mppi_shard_ipc_handle(self._h, mine))
@@ -62,6 +56,15 @@ class ShardedOptimizer(Optimizer):
             _raise_for(self._lib, self._h, self._lib.mppi_shard_open_peers(self._h, handles))
             dist.barrier(group=group)      # every mailbox is open everywhere before the first exchange
             self._peer_exchange = True
+        self._stream = None
+        if not self._peer_exchange:
+            # Kernels and torch.distributed collectives must be ordered on ONE stream.  The legacy default stream has
+            # handle 0, which mppi_set_stream reads as "the handle's own stream": kernels and collectives would then
+            # run unordered (ranks diverge).  So a dedicated torch stream is used unless the caller made one current.
+            cur = torch.cuda.current_stream()
+            self._stream = cur if cur.cuda_stream != 0 else torch.cuda.Stream()
+            _raise_for(self._lib, self._h, self._lib.mppi_set_stream(self._h, self._stream.cuda_stream))
+            self._bind_exchange_buffers()
 
     def _bind_exchange_buffers(self) -> None:
         """Views of the library's exchange buffers for the torch.distributed collectives.  The library re-allocates
@@ -81,7 +84,8 @@ class ShardedOptimizer(Optimizer):
         if int(cfg.n_robots) != 1 or int(cfg.shard_world) != self.world:
             raise ValueError("n_robots / shard_world cannot change on a live sharded handle")
         super().setConfig(cfg)
-        self._bind_exchange_buffers()
+        if not self._peer_exchange:
+            self._bind_exchange_buffers()
 
     def evalControl(self, inp: CycleInput, raise_on_failure: bool = True) -> CycleResult:
         lib, h = self._lib, self._h

@@ -41,10 +41,11 @@ def test_c3_full_shape_tensors_cells_and_flags(model, footprint):
     command, control sequence, optimal trajectory within tolerance."""
     cfg = _c3_config(model, footprint, materialize_tensors=1, visualize=1, debug_cells=1)
     cells = build_map("blocks", seed=3, inscribed=cfg.inscribed_radius, n_blocks=40, clear_radius=0.6)
-    cells[203:213, 216:220] = 254            # a lethal block 0.8 m ahead, inscribed ring around it: some candidates collide
-    ring = cells[201:215, 214:222]
+    # a lethal block 0.3 m ahead with an inscribed ring around it: the candidates that advance furthest collide (the
+    # first cycles start from a zero control sequence: displacements are a ~0.1 m random walk)
+    ring = cells[196:208, 204:211]
     ring[ring < 253] = 253
-    cells[203:213, 216:220] = 254
+    cells[198:206, 206:209] = 254
     pair = Pair(cfg, cells)
     path = S.arc_path((10.0, 10.0, 0.3), n_points=120, curvature=-0.2)
     drive(pair, path, (10.0, 10.0, 0.3), (0.1, 0.0, 0.0), cycles=2, label=f"C3-16384x100-{model}-fp{footprint}",

@@ -58,6 +58,8 @@ def main():
             e.setCostmap(cells, 0.05, 0.0, 0.0)
         del noise
 
+    # rank 0 has just spent seconds on the oracle's set-up: an exchange waits 2 s for its peers, so start together
+    dist.barrier()
     pose, speed = [10.0, 10.0, 0.0], (0.2, 0.0, 0.0)
     worst = 0.0
     for cycle in range(cycles):
@@ -100,6 +102,7 @@ def main():
     cfg2 = P.nav2_bringup_config(batch_size=batch, shard_world=world, shard_rank=rank, temperature=0.25)
     inp = nb.CycleInput(pose=tuple(pose), speed=speed, path=path, goal=tuple(path[-1]), goal_checker_xy_tolerance=0.25)
     after = {}
+    dist.barrier()
     for mode, eng in engines.items():
         eng.setConfig(cfg2)
         after[mode] = eng.evalControl(inp)
