@@ -378,6 +378,9 @@ int mppi_score_tensors(
 
 /* Copies one tensor of the last optimize()/score call to host memory (dst_bytes must match). */
 int mppi_get_tensor(MppiHandle * h, uint32_t robot, int32_t which, void * dst, size_t dst_bytes);
+/* How many entries of the critic list the last optimize() iteration evaluated before fail_flag stopped the loop
+ * (CriticManager::evalTrajectoriesScores, critic_manager.cpp:89-93): the critics CriticsStats reports (:101-117). */
+int mppi_get_critics_evaluated(MppiHandle * h, uint32_t robot, uint32_t * n_evaluated);
 /* Current control sequence (after the last evalControl's shift), 3 x T floats: vx, vy, wz. */
 int mppi_get_control_sequence(MppiHandle * h, uint32_t robot, float * vx, float * vy, float * wz);
 int mppi_set_control_sequence(

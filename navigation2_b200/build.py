@@ -92,6 +92,8 @@ def build_host(force: bool = False, verbose: bool = False) -> str:
     hdrs = [os.path.join(HOST, "include", "nav2_mppi_controller_b200", "mppi.hpp"),
             os.path.join(HOST, "include", "ros_shim", "ros_shim.hpp"), os.path.join(ROOT, "include", "mppi_b200.h"),
             os.path.join(HOST, "include", "nav2_costmap_2d_b200", "inflation_layer.hpp"),
+            os.path.join(HOST, "include", "nav2_controller_b200", "feasible_path_handler.hpp"),
+            os.path.join(HOST, "include", "nav2_controller_b200", "fleet_controller_server.hpp"),
             os.path.join(ROOT, "include", "costmap_inflation_b200.h")]
     test_src = os.path.join(HOST, "test", "test_host.cpp")
     inc = ["-I", os.path.join(HOST, "include"), "-I", os.path.join(ROOT, "include")]

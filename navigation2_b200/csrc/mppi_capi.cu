@@ -457,7 +457,8 @@ int allocate(MppiHandle * h)
   CU_CHECK(h, cudaMalloc(&h->d_obs_raw, R * B * sizeof(float)));
   CU_CHECK(h, cudaMalloc(&h->d_obs_rep, R * B * sizeof(float)));
   CU_CHECK(h, cudaMalloc(&h->d_last, R * 3 * B * sizeof(float)));
-  CU_CHECK(h, cudaMalloc(&h->d_pa, std::max<size_t>(4, R * B * static_cast<size_t>((3 * h->n_pa + 3) & ~3)) * sizeof(float)));
+  // one row per trajectory plus a spare row (where the tail threads of k_rollout_lean's last block park their stores)
+  CU_CHECK(h, cudaMalloc(&h->d_pa, std::max<size_t>(4, (R * B + 1) * static_cast<size_t>((3 * h->n_pa + 3) & ~3)) * sizeof(float)));
   CU_CHECK(h, cudaMalloc(&h->d_costs, R * B * sizeof(float)));
   CU_CHECK(h, cudaMalloc(&h->d_softmax, R * B * sizeof(float)));
   CU_CHECK(h, cudaMemset(h->d_costs, 0, R * B * sizeof(float)));
@@ -912,7 +913,7 @@ LaunchPlan make_plan(MppiHandle * h)
   if (h->B % 4 != 0) {stages = 0;}
   p.sm_a = mppi_smem_layout_a(h->T, need ? p.path_cap : 0, obstacles, ring, p.block_a, win_bytes, axes, stages);
   p.sm_tensors = mppi_smem_layout_a(h->T, need ? p.path_cap : 0, obstacles, 0, p.block_a, win_bytes, axes, 0);
-  p.block_b = 128;
+  p.block_b = MPPI_BLOCK_B;
   // kernel instantiation: union of the active critics' types over the robots of this call
   uint32_t types = 0;
   for (int r = 0; r < h->R; ++r) {
@@ -936,6 +937,13 @@ LaunchPlan make_plan(MppiHandle * h)
     for (int r = 0; r < h->R && ok; ++r) {
       const float res = static_cast<float>(h->robots[r].resolution);
       ok = res >= 0x1p-60f && res <= 0x1p60f;
+      // the heading stays far inside mppi_sincosf's range over the whole horizon: |wz(t)| <= |wz(0)| + t * max_delta_wz
+      // (MotionModel::predict clamps every step, whatever the noise), so |yaw(t)| <= |yaw(0)| + T dt (|wz(0)| + T max_delta_wz)
+      const DevCycle & cy = *h->hcyc(r);
+      const double horizon = static_cast<double>(h->T) * h->cfg.model_dt;
+      const double bound = std::fabs(static_cast<double>(cy.pose_yaw)) +
+        horizon * (std::fabs(static_cast<double>(cy.speed_wz)) + h->T * static_cast<double>(h->h_static.max_delta_wz));
+      ok = ok && bound < 1.0e6;   // NaN fails the comparison
     }
     p.ka.lean_ok = ok;
   }
@@ -1954,6 +1962,15 @@ int mppi_get_tensor(MppiHandle * h, uint32_t robot, int32_t which, void * dst, s
   if (bytes != dst_bytes) {h->error = "dst_bytes does not match the tensor size"; return MPPI_ERR_INVALID_ARGUMENT;}
   CU_CHECK(h, cudaStreamSynchronize(h->stream));
   CU_CHECK(h, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return MPPI_OK;
+}
+
+int mppi_get_critics_evaluated(MppiHandle * h, uint32_t robot, uint32_t * n_evaluated)
+{
+  if (!h || robot >= static_cast<uint32_t>(h->R) || !n_evaluated) {return MPPI_ERR_INVALID_ARGUMENT;}
+  CU_CHECK(h, cudaStreamSynchronize(h->stream));
+  const DevOutHeader * hdr = reinterpret_cast<const DevOutHeader *>(h->h_out + static_cast<size_t>(robot) * h->out_stride);
+  *n_evaluated = static_cast<uint32_t>(std::max(0, std::min<int>(hdr->critics_evaluated, static_cast<int>(h->cfg.n_critics))));
   return MPPI_OK;
 }
 

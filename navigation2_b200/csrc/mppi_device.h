@@ -11,6 +11,7 @@
 
 #define MPPI_MAX_PATH_POINTS 2048
 #define MPPI_BLOCK_A 256        // rollout+score kernel, throughput mode: threads per block (one trajectory each)
+#define MPPI_BLOCK_B 128        // path-critics kernel: threads per block (eight resident blocks per SM)
 #define MPPI_BLOCK_C 256        // softmax partial kernel
 #define MPPI_TCHUNK 8           // time steps reduced together in the softmax partial kernel
 #define MPPI_TCHUNK_A 8         // time steps per bulk-async stage of the rollout kernel
@@ -139,7 +140,9 @@ struct DevOutHeader
   int32_t map_miss;   // a lookup fell outside the uploaded costmap window while the full map was not resident:
                       // nothing was committed (control sequence, filter history); the host uploads the map and reruns
   uint32_t seq;       // DevCycle::seq of the cycle these results belong to, written LAST behind a system-scope fence
-  int32_t pad[2];
+  int32_t critics_evaluated;  // how many entries of the critic list CriticManager::evalTrajectoriesScores walked before
+                              // fail_flag stopped it (critic_manager.cpp:89-93): n_critics if it never did
+  int32_t pad[1];
 };
 
 struct KArgs

@@ -32,6 +32,37 @@ struct TwistStamped {std_msgs::msg::Header header; Twist twist;};
 
 namespace nav_msgs::msg {struct Path {std_msgs::msg::Header header; std::vector<geometry_msgs::msg::PoseStamped> poses;};}
 
+namespace std_msgs::msg {struct ColorRGBA {float r{0}, g{0}, b{0}, a{0};};}
+namespace visualization_msgs::msg
+{
+struct Marker
+{
+  static constexpr int32_t SPHERE = 2, LINE_STRIP = 4;
+  static constexpr int32_t ADD = 0;
+  std_msgs::msg::Header header;
+  std::string ns;
+  int32_t id{0};
+  int32_t type{0};
+  int32_t action{0};
+  geometry_msgs::msg::Pose pose;
+  geometry_msgs::msg::Vector3 scale;
+  std_msgs::msg::ColorRGBA color;
+  std::vector<geometry_msgs::msg::Point> points;
+};
+struct MarkerArray {std::vector<Marker> markers;};
+}  // namespace visualization_msgs::msg
+// nav2_msgs/msg/CriticsStats.msg
+namespace nav2_msgs::msg
+{
+struct CriticsStats
+{
+  builtin_interfaces::msg::Time stamp;
+  std::vector<std::string> critics;
+  std::vector<bool> changed;
+  std::vector<float> costs_sum;
+};
+}  // namespace nav2_msgs::msg
+
 namespace tf2
 {
 // tf2::getYaw(quaternion) (geometry2 tf2/utils.h): yaw of a unit quaternion
@@ -63,6 +94,16 @@ class NoValidControl : public ControllerException
 {
 public:
   explicit NoValidControl(const std::string & description) : ControllerException(description) {}
+};
+class InvalidPath : public ControllerException
+{
+public:
+  explicit InvalidPath(const std::string & description) : ControllerException(description) {}
+};
+class ControllerTFError : public ControllerException
+{
+public:
+  explicit ControllerTFError(const std::string & description) : ControllerException(description) {}
 };
 
 // nav2_core/include/nav2_core/goal_checker.hpp:66-124 (the member the MPPI critics call)
@@ -97,7 +138,58 @@ private:
   std::string name_;
   std::map<std::string, ParameterValue> params_;
 };
-struct TransformBuffer {using SharedPtr = std::shared_ptr<TransformBuffer>;};
+// tf2_ros::Buffer stand-in: one planar transform per (target frame, source frame) pair; identity when none is set
+struct TransformBuffer
+{
+  using SharedPtr = std::shared_ptr<TransformBuffer>;
+  struct Planar {double x{0}, y{0}, yaw{0};};
+  void setTransform(const std::string & target_frame, const std::string & source_frame, double x, double y, double yaw)
+  {
+    transforms_[target_frame + "<-" + source_frame] = Planar{x, y, yaw};
+  }
+  // pose expressed in source_frame -> target_frame (nav2_util::transformPoseInTargetFrame)
+  bool transform(
+    const geometry_msgs::msg::PoseStamped & in, geometry_msgs::msg::PoseStamped & out, const std::string & target_frame) const
+  {
+    out = in;
+    out.header.frame_id = target_frame;
+    if (in.header.frame_id == target_frame || in.header.frame_id.empty() || target_frame.empty()) {return true;}
+    auto it = transforms_.find(target_frame + "<-" + in.header.frame_id);
+    if (it == transforms_.end()) {return false;}
+    const Planar & t = it->second;
+    const double c = std::cos(t.yaw), s = std::sin(t.yaw);
+    out.pose.position.x = t.x + c * in.pose.position.x - s * in.pose.position.y;
+    out.pose.position.y = t.y + s * in.pose.position.x + c * in.pose.position.y;
+    out.pose.orientation = tf2::quaternionFromYaw(tf2::getYaw(in.pose.orientation) + t.yaw);
+    return true;
+  }
+
+private:
+  std::map<std::string, Planar> transforms_;
+};
+
+// rclcpp_lifecycle::LifecyclePublisher stand-in: keeps the last message, counts what was published; subscribers are a number
+template<typename MsgT>
+class Publisher
+{
+public:
+  explicit Publisher(std::string topic) : topic_(std::move(topic)) {}
+  void on_activate() {active_ = true;}
+  void on_deactivate() {active_ = false;}
+  size_t get_subscription_count() const {return subscribers_;}
+  void setSubscriptionCount(size_t n) {subscribers_ = n;}
+  void publish(std::unique_ptr<MsgT> msg) {last_ = std::move(msg); ++published_;}
+  const MsgT * last() const {return last_.get();}
+  size_t publishedCount() const {return published_;}
+  const std::string & topic() const {return topic_;}
+
+private:
+  std::string topic_;
+  bool active_{false};
+  size_t subscribers_{1};
+  size_t published_{0};
+  std::unique_ptr<MsgT> last_;
+};
 }  // namespace nav2
 
 namespace nav2_costmap_2d
@@ -125,6 +217,15 @@ public:
   unsigned char getCost(unsigned int mx, unsigned int my) const {return cells_[getIndex(mx, my)];}
   void setCost(unsigned int mx, unsigned int my, unsigned char c) {cells_[getIndex(mx, my)] = c;}
   mutex_t * getMutex() {return &mutex_;}
+  double getSizeInMetersX() const {return size_x_ * resolution_;}   // costmap_2d.cpp:558-566
+  double getSizeInMetersY() const {return size_y_ * resolution_;}
+  bool worldToMap(double wx, double wy, unsigned int & mx, unsigned int & my) const  // costmap_2d.cpp:292-305
+  {
+    if (wx < origin_x_ || wy < origin_y_) {return false;}
+    mx = static_cast<unsigned int>((wx - origin_x_) / resolution_);
+    my = static_cast<unsigned int>((wy - origin_y_) / resolution_);
+    return mx < size_x_ && my < size_y_;
+  }
 
 private:
   unsigned int size_x_, size_y_;

@@ -4,12 +4,17 @@
 // reference's controller_state_transition_test.cpp and optimizer_smoke_test.cpp.
 //   test_host config            parameter parsing / exceptions only (no GPU needed)
 //   test_host run <model> <n>   n closed-loop cycles on the GPU; prints "cmd vx vy wz" per cycle
+//   test_host pathhandler       FeasiblePathHandler mirror, the reference's path_handler.cpp cases (no GPU needed)
+//   test_host visualize <n>     `visualize: true`: CriticsStats + TrajectoryVisualizer output of the last of n cycles (GPU)
+//   test_host fleet <R> <n>     FleetControllerServer: R robots, n cycles, one optimiser call per cycle (GPU)
+//   test_host score             CriticFunction::score on caller tensors (GPU)
 //   test_host inflate           the InflationLayer mirror on the GPU: the cases of inflation_tests.cpp, prints the grids
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 
+#include "nav2_controller_b200/fleet_controller_server.hpp"
 #include "nav2_costmap_2d_b200/inflation_layer.hpp"
 #include "nav2_mppi_controller_b200/mppi.hpp"
 
@@ -101,6 +106,45 @@ int testConfig()
     cm3.on_configure(node2, name, costmap_ros, &ph2);
   } catch (const nav2_core::ControllerException &) {threw = true;}
   EXPECT(threw);
+  // ParametersHandler: a static parameter cannot change at run time, a pre-callback can veto a dynamic one
+  // (parameters_handler.cpp:59-93), post-callbacks run after an accepted update (:95-127)
+  {
+    auto node3 = makeNode("diff_drive");
+    mppi::ParametersHandler ph3(node3, name);
+    std::vector<std::string> critics;
+    float vx_max = 0.0f;
+    int posts = 0;
+    bool limit_active = true;
+    ph3.getParamGetter(name)(critics, "critics", std::vector<std::string>{}, mppi::ParameterType::Static);
+    ph3.getParamGetter(name)(vx_max, "vx_max", 0.5f);
+    ph3.addPreCallback(name + ".vx_max", [&](const std::string & n, const nav2::ParameterValue &, mppi::SetParametersResult & r) {
+        if (limit_active) {r.successful = false; r.reason += "Rejected dynamic update to '" + n + "': speed limit is active.";}
+      });
+    ph3.addPostCallback([&]() {++posts;});
+    auto r1 = ph3.setDynamic(name + ".critics", std::vector<std::string>{"CostCritic"});
+    EXPECT(!r1.successful && r1.reason.find("static parameter") != std::string::npos && posts == 0);
+    auto r2 = ph3.setDynamic(name + ".vx_max", 0.8);
+    EXPECT(!r2.successful && posts == 0);
+    EXPECT(std::get<double>(node3->get_parameter(name + ".vx_max")) == 0.5);
+    limit_active = false;
+    auto r3 = ph3.setDynamic(name + ".vx_max", 0.8);
+    EXPECT(r3.successful && posts == 1);
+    EXPECT(std::get<double>(node3->get_parameter(name + ".vx_max")) == 0.8);
+    EXPECT(ph3.setDynamic("other_plugin.vx_max", 0.1).successful && posts == 1);   // not this plugin's parameter
+  }
+  // Ackermann applyConstraints (motion_models.hpp:292-298; motion_model_tests.cpp): |wz| <= |vx| / min_turning_r
+  {
+    mppi::AckermannMotionModel ack;
+    mppi::ControlSequence cs;
+    cs.vx = {1.0f, 0.1f, -0.4f}; cs.vy = {0, 0, 0}; cs.wz = {10.0f, -1.0f, 0.5f};
+    ack.applyConstraints(cs);
+    EXPECT(cs.wz[0] == 5.0f && cs.wz[1] == -0.5f && cs.wz[2] == 0.5f);
+    mppi::DiffDriveMotionModel dd;
+    mppi::models::State st;
+    bool t2 = false;
+    try {dd.predict(st);} catch (const nav2_core::ControllerException &) {t2 = true;}
+    EXPECT(t2);
+  }
   EXPECT(std::fabs(tf2::getYaw(tf2::quaternionFromYaw(0.7)) - 0.7) < 1e-12);
   EXPECT(std::fabs(tf2::getYaw(tf2::quaternionFromYaw(-2.9)) + 2.9) < 1e-12);
   std::printf("config ok\n");
@@ -156,6 +200,270 @@ int testRun(const std::string & model, int cycles)
   controller.deactivate();
   controller.cleanup();
   std::printf("run ok\n");
+  return 0;
+}
+// nav2_controller/plugins/test/path_handler.cpp: GetAndPrunePath (:81-103), TestBounds (:105-151),
+// SearchDistanceSmallerThanPoseSpacing (:153-193), TestTransforms (:250-293), through the mirror
+int testPathHandler()
+{
+  auto makeRos = []() {
+      // Costmap2DROS defaults: 5 m x 5 m @0.1 m (costmap_2d_ros.cpp:403-417), global frame "odom"
+      auto costmap = std::make_shared<nav2_costmap_2d::Costmap2D>(50, 50, 0.1, 0.0, 0.0, 0);
+      return std::make_shared<nav2_costmap_2d::Costmap2DROS>(costmap, true, std::vector<geometry_msgs::msg::Point>{});
+    };
+  auto tf = std::make_shared<nav2::TransformBuffer>();
+  tf->setTransform("map", "odom", 0.0, 0.0, 0.0);
+  tf->setTransform("odom", "map", 0.0, 0.0, 0.0);
+  {
+    auto node = std::make_shared<nav2::LifecycleNode>("my_node");
+    node->declare_parameter("dummy.max_robot_pose_search_dist", 99999.9);
+    nav2_controller::FeasiblePathHandler handler;
+    handler.initialize(node, "dummy", makeRos(), tf);
+    EXPECT(handler.getCostmapMaxExtent() == 2.5);
+    nav_msgs::msg::Path path;
+    path.header.frame_id = "map";
+    path.poses.resize(100);
+    for (unsigned int i = 0; i != path.poses.size(); i++) {
+      path.poses[i].pose.position.x = i;
+      path.poses[i].header.frame_id = "map";
+    }
+    handler.setPlan(path);
+    EXPECT(handler.getPlan().poses.size() == 100u && handler.getPlan().header.frame_id == "map");
+    geometry_msgs::msg::PoseStamped robot_pose;
+    robot_pose.header.frame_id = "odom";
+    robot_pose.pose.position.x = 25.0;
+    auto segment = handler.findPlanSegment(robot_pose);
+    // the closest pose lies outside the 5 m costmap: nothing survives the transform (InvalidPath), the plan is still pruned
+    bool threw = false;
+    try {handler.transformLocalPlan(segment.start, segment.end);} catch (const nav2_core::InvalidPath &) {threw = true;}
+    EXPECT(threw);
+    EXPECT(handler.remainingPoses() == 75u);
+    // inside the costmap: poses every 0.5 m from the origin, robot at 1.2 m; prune_distance 2.0 m ahead
+    nav_msgs::msg::Path near;
+    near.header.frame_id = "map";
+    near.poses.resize(20);
+    for (unsigned int i = 0; i != near.poses.size(); i++) {
+      near.poses[i].pose.position.x = 0.5 * i; near.poses[i].pose.position.y = 1.0;
+      near.poses[i].header.frame_id = "map";
+    }
+    handler.setPlan(near);
+    robot_pose.pose.position.x = 1.2; robot_pose.pose.position.y = 1.0;
+    segment = handler.findPlanSegment(robot_pose);
+    auto local = handler.transformLocalPlan(segment.start, segment.end);
+    EXPECT(local.header.frame_id == "odom");
+    EXPECT(local.poses.front().pose.position.x == 1.0);          // closest pose (1.0 is 0.2 away, 1.5 is 0.3 away)
+    EXPECT(local.poses.size() == 5u);                            // 1.0 .. 3.0: the first pose MORE than 2.0 m along ends it
+    EXPECT(handler.remainingPoses() == 18u);                     // poses 0.0 and 0.5 were pruned
+    EXPECT(handler.getTransformedGoal(robot_pose.header.stamp).pose.position.x == 9.5);
+    // the local plan stops at the costmap border (5 m): start close to it
+    robot_pose.pose.position.x = 4.1;
+    segment = handler.findPlanSegment(robot_pose);
+    local = handler.transformLocalPlan(segment.start, segment.end);
+    EXPECT(local.poses.front().pose.position.x == 4.0 && local.poses.back().pose.position.x == 4.5);
+  }
+  {
+    auto node = std::make_shared<nav2::LifecycleNode>("my_node");
+    node->declare_parameter("dummy.max_robot_pose_search_dist", 0.5);
+    nav2_controller::FeasiblePathHandler handler;
+    handler.initialize(node, "dummy", makeRos(), tf);
+    nav_msgs::msg::Path path;
+    path.header.frame_id = "map";
+    path.poses.resize(3);
+    for (unsigned int i = 0; i != path.poses.size(); ++i) {
+      path.poses[i].pose.position.x = i;
+      path.poses[i].header.frame_id = "map";
+    }
+    geometry_msgs::msg::PoseStamped robot_pose;
+    robot_pose.header.frame_id = "odom";
+    robot_pose.pose.position.x = 0.9;
+    handler.setPlan(path);
+    auto segment = handler.findPlanSegment(robot_pose);
+    auto local = handler.transformLocalPlan(segment.start, segment.end);
+    EXPECT(local.poses.size() == 3u && local.poses.front().pose.position.x == 0.0);   // closest == begin, end == end
+  }
+  {
+    // TestTransforms: no transform into the plan's frame -> ControllerTFError; empty plan -> InvalidPath
+    auto node = std::make_shared<nav2::LifecycleNode>("my_node");
+    nav2_controller::FeasiblePathHandler handler;
+    handler.initialize(node, "dummy", makeRos(), tf);
+    geometry_msgs::msg::PoseStamped robot_pose;
+    robot_pose.header.frame_id = "nowhere";
+    bool threw = false;
+    try {handler.transformToGlobalPlanFrame(robot_pose);} catch (const nav2_core::InvalidPath &) {threw = true;}
+    EXPECT(threw);
+    nav_msgs::msg::Path path;
+    path.header.frame_id = "map";
+    path.poses.resize(2);
+    handler.setPlan(path);
+    threw = false;
+    try {handler.transformToGlobalPlanFrame(robot_pose);} catch (const nav2_core::ControllerTFError &) {threw = true;}
+    EXPECT(threw);
+    robot_pose.header.frame_id = "odom";
+    handler.transformToGlobalPlanFrame(robot_pose);
+  }
+  std::printf("pathhandler ok\n");
+  return 0;
+}
+
+// `visualize: true`: the host half of SURVEY.md section 8f row 1.  Prints what was published so the Python test can
+// compare it with the oracle's tensors: CriticsStats, the candidate-trajectory markers, the optimal path.
+int testVisualize(int cycles)
+{
+  auto node = makeNode("diff_drive");
+  node->declare_parameter("FollowPath.visualize", true);
+  node->declare_parameter("FollowPath.iteration_count", 1);
+  node->set_parameter("FollowPath.iteration_count", 1);
+  node->declare_parameter("FollowPath.TrajectoryVisualizer.trajectory_step", 50);
+  node->declare_parameter("FollowPath.TrajectoryVisualizer.time_step", 5);
+  auto costmap_ros = makeCostmap(true);
+  nav2_mppi_controller::MPPIController controller;
+  controller.configure(node, "FollowPath", nullptr, costmap_ros);
+  controller.activate();
+  nav_msgs::msg::Path path;
+  for (int i = 0; i < 50; ++i) {
+    geometry_msgs::msg::PoseStamped p;
+    p.pose.position.x = 0.5 + 0.05 * i;
+    p.pose.position.y = 0.5 + 0.02 * i;
+    p.pose.orientation = tf2::quaternionFromYaw(0.38);
+    path.poses.push_back(p);
+  }
+  geometry_msgs::msg::PoseStamped pose;
+  pose.pose.position.x = 0.5; pose.pose.position.y = 0.5;
+  pose.pose.orientation = tf2::quaternionFromYaw(0.3);
+  geometry_msgs::msg::Twist speed;
+  TestGoalChecker goal_checker;
+  for (int i = 0; i < cycles; ++i) {
+    auto cmd = controller.computeVelocityCommands(pose, speed, &goal_checker, path, path.poses.back());
+    std::printf("cmd %.9g %.9g %.9g\n", cmd.twist.linear.x, cmd.twist.linear.y, cmd.twist.angular.z);
+  }
+  auto * stats_pub = controller.optimizer().getCriticManager().criticsEffectPublisher();
+  EXPECT(stats_pub != nullptr && stats_pub->publishedCount() == static_cast<size_t>(cycles));
+  const auto * stats = stats_pub->last();
+  EXPECT(stats->critics.size() == 8 && stats->critics[1] == "CostCritic");
+  for (size_t k = 0; k < stats->critics.size(); ++k) {
+    std::printf("stat %s %d %.9g\n", stats->critics[k].c_str(), stats->changed[k] ? 1 : 0, stats->costs_sum[k]);
+  }
+  auto & viz = controller.trajectoryVisualizer();
+  EXPECT(viz.trajectoriesPublisher()->publishedCount() == static_cast<size_t>(cycles));
+  const auto * markers = viz.trajectoriesPublisher()->last();
+  EXPECT(markers->markers.size() == 2000 / 50 + 56);             // 40 candidates + 56 optimal-trajectory spheres
+  for (const auto & m : markers->markers) {
+    if (m.ns != "Candidate Trajectories") {continue;}
+    EXPECT(m.type == visualization_msgs::msg::Marker::LINE_STRIP && m.points.size() == 12);   // ceil(56 / 5)
+    std::printf("traj %d %.6g %.6g %.6g %.6g", m.id, m.color.r, m.color.g, m.color.b, m.color.a);
+    for (const auto & p : m.points) {std::printf(" %.9g %.9g", p.x, p.y);}
+    std::printf("\n");
+  }
+  const auto * optimal = viz.optimalPathPublisher()->last();
+  EXPECT(optimal->poses.size() == 56 && optimal->header.frame_id == "odom");
+  const auto & traj = controller.lastOptimalTrajectory();
+  for (size_t i = 0; i < traj.size(); ++i) {
+    EXPECT(optimal->poses[i].pose.position.x == traj[i][0] && optimal->poses[i].pose.position.y == traj[i][1]);
+  }
+  // a dynamic parameter update goes through the pre-callbacks: rejected while a speed limit is active
+  // (optimizer.cpp:85-103), accepted and applied (new device configuration, reset) once it is cleared
+  controller.setSpeedLimit(50.0, true);
+  EXPECT(controller.optimizer().isSpeedLimitActive());
+  mppi::ParametersHandler * ph = nullptr;
+  (void)ph;
+  controller.deactivate();
+  controller.cleanup();
+  std::printf("visualize ok\n");
+  return 0;
+}
+
+// The fleet-level caller: N robots, each with its own costmap, plan and pose, one call (fleet_controller_server.hpp).
+// Prints "fleet <robot> <valid> vx vy wz n_local_plan" per robot and cycle.
+int testFleet(int n_robots, int cycles)
+{
+  auto node = makeNode("diff_drive");
+  node->set_parameter("FollowPath.iteration_count", 1);
+  std::vector<std::shared_ptr<nav2_costmap_2d::Costmap2DROS>> costmaps;
+  for (int r = 0; r < n_robots; ++r) {
+    auto ros = makeCostmap(true);
+    auto * c = ros->getCostmap();
+    for (unsigned int i = 0; i < 6; ++i) {
+      for (unsigned int j = 0; j < 6; ++j) {c->setCost((7 * r + 3 * i) % 40, (11 * r + 5 * j) % 40, 120);}   // a different map per robot
+    }
+    costmaps.push_back(ros);
+  }
+  nav2_controller::FleetControllerServer server;
+  server.configure(node, "FollowPath", costmaps, nullptr);
+  std::vector<geometry_msgs::msg::PoseStamped> poses(n_robots);
+  std::vector<geometry_msgs::msg::Twist> speeds(n_robots);
+  std::vector<double> yaws(n_robots);
+  for (int r = 0; r < n_robots; ++r) {
+    nav_msgs::msg::Path path;
+    for (int i = 0; i < 60; ++i) {
+      geometry_msgs::msg::PoseStamped p;
+      p.pose.position.x = 0.4 + 0.05 * i;
+      p.pose.position.y = 0.4 + 0.01 * (r + 1) * i;
+      p.pose.orientation = tf2::quaternionFromYaw(std::atan2(0.01 * (r + 1), 0.05));
+      path.poses.push_back(p);
+    }
+    server.setPlan(r, path);
+    poses[r].pose.position.x = 0.5; poses[r].pose.position.y = 0.5 + 0.02 * r;
+    yaws[r] = 0.1 * r;
+  }
+  TestGoalChecker goal_checker;
+  for (int c = 0; c < cycles; ++c) {
+    for (int r = 0; r < n_robots; ++r) {poses[r].pose.orientation = tf2::quaternionFromYaw(yaws[r]);}
+    const auto cmds = server.computeVelocityCommands(poses, speeds, &goal_checker);
+    for (int r = 0; r < n_robots; ++r) {
+      std::printf("fleet %d %d %.9g %.9g %.9g %zu\n", r, cmds[r].valid ? 1 : 0, cmds[r].cmd.twist.linear.x,
+        cmds[r].cmd.twist.linear.y, cmds[r].cmd.twist.angular.z, cmds[r].local_plan.poses.size());
+      EXPECT(cmds[r].valid);
+      speeds[r] = cmds[r].cmd.twist;
+      poses[r].pose.position.x += speeds[r].linear.x * std::cos(yaws[r]) * 0.05;
+      poses[r].pose.position.y += speeds[r].linear.x * std::sin(yaws[r]) * 0.05;
+      yaws[r] += speeds[r].angular.z * 0.05;
+    }
+  }
+  std::printf("fleet ok\n");
+  return 0;
+}
+
+// CriticFunction::score on caller tensors through the mirror (critics_tests.cpp's shape of the call): every trajectory
+// stands still at (x0, y0); prints the costs the critic added.
+int testScore()
+{
+  auto node = makeNode("diff_drive");
+  auto costmap_ros = makeCostmap(true);
+  std::string name = "FollowPath";
+  mppi::ParametersHandler ph(node, name);
+  mppi::CriticManager cm;
+  cm.on_configure(node, name, costmap_ros, &ph);
+  const uint32_t B = 1000, T = 30;
+  mppi::models::State state;
+  state.batch_size = B; state.time_steps = T;
+  state.vx.assign(B * T, 0.0f); state.vy.assign(B * T, 0.0f); state.wz.assign(B * T, 0.0f);
+  mppi::models::Trajectories traj;
+  traj.x.assign(B * T, 1.0f); traj.y.assign(B * T, 1.0f); traj.yaws.assign(B * T, 0.0f);
+  for (uint32_t b = 0; b < B / 2; ++b) {                 // half of the batch sits on the cost-250 block
+    for (uint32_t t = 0; t < T; ++t) {traj.x[t * B + b] = 2.0f; traj.y[t * B + b] = 2.0f;}
+  }
+  nav_msgs::msg::Path path;
+  for (int i = 0; i < 30; ++i) {geometry_msgs::msg::PoseStamped p; p.pose.position.x = 0.2 * i; p.pose.position.y = 1.0; path.poses.push_back(p);}
+  geometry_msgs::msg::Pose goal = path.poses.back().pose;
+  std::vector<float> costs(B, 0.0f);
+  float model_dt = 0.1f;
+  state.local_path_length = 5.8f;
+  mppi::critics::CriticData data{state, traj, path, goal, costs, model_dt};
+  data.trajectories_in_collision.assign(B, false);
+  cm.critics()[1]->score(data);                          // CostCritic
+  EXPECT(!data.fail_flag);
+  EXPECT(costs[B - 1] == 0.0f);                          // free space adds nothing
+  EXPECT(costs[0] > 0.0f);
+  std::printf("score cost %.9g %.9g\n", costs[0], costs[B - 1]);
+  // cost_critic.cpp:223-228: every sample adds the cell cost 250 -> 250 * (3.81 / 254) for the stationary trajectory
+  EXPECT(std::fabs(costs[0] - 250.0f * (3.81f / 254.0f)) < 1e-4f);
+  const float before = costs[0];
+  cm.critics()[7]->score(data);                          // PreferForwardCritic: vx == 0 everywhere adds nothing
+  EXPECT(costs[0] == before);
+  for (uint32_t i = 0; i < B * T; ++i) {state.vx[i] = -0.2f;}
+  cm.critics()[7]->score(data);                          // backwards at 0.2 m/s: 5 * sum(0.2 * dt) = 5 * 0.2 * 0.1 * 30
+  EXPECT(std::fabs((costs[0] - before) - 5.0f * 0.2f * 0.1f * 30.0f) < 1e-4f);
+  std::printf("score ok\n");
   return 0;
 }
 }  // namespace
@@ -219,6 +527,10 @@ int main(int argc, char ** argv)
   try {
     if (argc >= 2 && std::strcmp(argv[1], "config") == 0) {return testConfig();}
     if (argc >= 2 && std::strcmp(argv[1], "inflate") == 0) {return testInflate();}
+    if (argc >= 2 && std::strcmp(argv[1], "pathhandler") == 0) {return testPathHandler();}
+    if (argc >= 3 && std::strcmp(argv[1], "visualize") == 0) {return testVisualize(std::atoi(argv[2]));}
+    if (argc >= 4 && std::strcmp(argv[1], "fleet") == 0) {return testFleet(std::atoi(argv[2]), std::atoi(argv[3]));}
+    if (argc >= 2 && std::strcmp(argv[1], "score") == 0) {return testScore();}
     if (argc >= 4 && std::strcmp(argv[1], "run") == 0) {return testRun(argv[2], std::atoi(argv[3]));}
   } catch (const std::exception & e) {
     std::printf("EXCEPTION: %s\n", e.what());
