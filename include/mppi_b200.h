@@ -322,6 +322,18 @@ int mppi_upload_costmap(
   MppiHandle * h, uint32_t robot, const uint8_t * cells, uint32_t size_x, uint32_t size_y,
   double resolution, double origin_x, double origin_y);
 
+/* The same hand-over for a costmap that already lives in DEVICE memory — the output of the inflation pass
+ * (costmap_inflation_update_costs_device, include/costmap_inflation_b200.h; reference producer:
+ * nav2_costmap_2d/plugins/inflation_layer.cpp:283-348, consumer: cost_critic.cpp:138-144).  `device_cells` is
+ * row-major uint8 with `row_pitch` bytes between rows; it is copied device-to-device into the handle's own storage on
+ * the handle's stream, ordered after everything enqueued so far on `producer_stream` (a cudaStream_t; NULL = the
+ * caller has synchronised).  Nothing crosses PCIe and the host never sees the cells: path validity
+ * (utils::findPathCosts) is then evaluated on the device.  Replaced by the next mppi_upload_costmap /
+ * mppi_optimize_in_place for that robot. */
+int mppi_set_costmap_device(
+  MppiHandle * h, uint32_t robot, const uint8_t * device_cells, uint32_t size_x, uint32_t size_y, size_t row_pitch,
+  double resolution, double origin_x, double origin_y, void * producer_stream);
+
 /* Reference-noise injection: replaces NoiseGenerator::noises_vx_/vy_/wz_ (noise_generator.hpp:96-98).
  * Each pointer is B_local x T column-major host memory; nvy may be NULL (zeros, as for
  * non-holonomic models).  Injected noise survives reset() until mppi_generate_noise is called. */

@@ -223,6 +223,7 @@ SYMBOLS = {
     "mppi_set_resident_capture": (C.c_int, [_P, C.c_int]),
     "mppi_time_e2e": (C.c_int, [_P, _U8, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double,
                                 C.POINTER(MppiCycleIn), C.POINTER(MppiCycleOut), C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "mppi_set_costmap_device": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, C.c_size_t, C.c_double, C.c_double, C.c_double, _P]),
     "mppi_get_critics_evaluated": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "mppi_time_e2e_views": (C.c_int, [_P, C.POINTER(MppiCostmapView), C.POINTER(MppiCycleIn), C.POINTER(MppiCycleOut), C.c_int,
                                       C.POINTER(C.c_double)]),

@@ -55,6 +55,7 @@ struct HostRobot
   const uint8_t * map_src = nullptr;
   uint32_t map_src_pitch = 0;
   bool staged_current = false;   // the staging slab holds the costmap of the current cycle
+  bool device_only = false;      // the costmap was handed over in device memory (mppi_set_costmap_device): no host copy exists
 };
 
 #define CU_CHECK(h, call) \
@@ -573,6 +574,11 @@ int ensure_arena(MppiHandle * h, size_t need_stride, int need_path)
         if (rb.map_src == rb.map_host) {rb.map_src = nh + stride * r;}
         rb.map_host = nh + stride * r;
         rb.device_stale = true;
+      } else if (rb.map_valid && rb.device_only && h->d_arena) {
+        // a map that exists only on the device moves with the arena
+        if (cudaMemcpy(nd + stride * r, h->d_arena + h->map_stride * r, rb.map_bytes, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+          rb.map_valid = false;
+        }
       }
       rb.stage_pending = false;  // both streams are idle
     }
@@ -722,7 +728,8 @@ int prepare_robot(MppiHandle * h, int r, const MppiCycleIn & in, int preset_furt
   // utils::findPathCosts (tools/utils.hpp:358-387): validity of path points 0 .. n-2
   uint8_t * valid = h->hvalid(r);
   std::memset(valid, 0, h->max_path);
-  for (int i = 0; i + 1 < n; ++i) {
+  cy.valid_on_device = rb.device_only ? 1 : 0;   // no host copy of the map: the kernels evaluate the same rule
+  for (int i = 0; !rb.device_only && i + 1 < n; ++i) {
     const double wx = px[i], wy = py[i];
     bool ok = false;
     if (!(wx < rb.origin_x || wy < rb.origin_y)) {
@@ -1446,6 +1453,7 @@ int stage_map(
     }
   }
   rb.map_host = stage;
+  rb.device_only = false;
   rb.staged_current = true;
   rb.map_src = stage; rb.map_src_pitch = pitch;
   rb.size_x = size_x; rb.size_y = size_y; rb.pitch = pitch;
@@ -1477,6 +1485,47 @@ int mppi_upload_costmap(
     if (rc != MPPI_OK) {return rc;}
   }
   if (h->host_timers) {h->ht[0] += std::chrono::duration<double>(std::chrono::steady_clock::now() - ht0).count();}
+  return MPPI_OK;
+}
+
+// The costmap handed over where a device-side producer left it (the inflation pass, costmap_inflation_update_costs_device):
+// one device-to-device 2-D copy into the robot's slab of the arena, ordered after the producer's stream by an event.
+// No byte of the map crosses PCIe; the host keeps no copy, so path validity (utils::findPathCosts) is evaluated by the
+// kernels (DevCycle::valid_on_device) and single-launch cycles read their window from the resident map.
+int mppi_set_costmap_device(
+  MppiHandle * h, uint32_t robot, const uint8_t * device_cells, uint32_t size_x, uint32_t size_y, size_t row_pitch,
+  double resolution, double origin_x, double origin_y, void * producer_stream)
+{
+  if (!h || !device_cells || robot >= static_cast<uint32_t>(h->R) || size_x == 0 || size_y == 0 || row_pitch < size_x ||
+    !(resolution > 0.0))
+  {
+    if (h) {h->error = "bad costmap arguments";}
+    return MPPI_ERR_INVALID_ARGUMENT;
+  }
+  const uint32_t pitch = (size_x + 15u) & ~15u;
+  const size_t need = static_cast<size_t>(pitch) * size_y;
+  if (need > h->map_stride) {
+    int arc = ensure_arena(h, need, h->max_path);
+    if (arc != MPPI_OK) {return arc;}
+  }
+  HostRobot & rb = h->robots[robot];
+  if (producer_stream != nullptr && static_cast<cudaStream_t>(producer_stream) != h->stream) {
+    if (!rb.stage_event) {CU_CHECK(h, cudaEventCreateWithFlags(&rb.stage_event, cudaEventDisableTiming));}
+    CU_CHECK(h, cudaEventRecord(rb.stage_event, static_cast<cudaStream_t>(producer_stream)));
+    CU_CHECK(h, cudaStreamWaitEvent(h->stream, rb.stage_event, 0));
+  }
+  uint8_t * dst = h->d_map + h->map_stride * robot;
+  if (pitch != size_x) {CU_CHECK(h, cudaMemsetAsync(dst, 0, need, h->stream));}   // row padding reads as free space
+  CU_CHECK(h, cudaMemcpy2DAsync(dst, pitch, device_cells, row_pitch, size_x, size_y, cudaMemcpyDeviceToDevice, h->stream));
+  rb.size_x = size_x; rb.size_y = size_y; rb.pitch = pitch;
+  rb.resolution = resolution; rb.origin_x = origin_x; rb.origin_y = origin_y;
+  rb.map_bytes = need;
+  rb.map_valid = true;
+  rb.device_stale = false;      // the device copy IS the map
+  rb.device_only = true;
+  rb.staged_current = false;
+  rb.map_src = nullptr; rb.map_src_pitch = 0; rb.map_host = nullptr;
+  rb.stage_pending = false;
   return MPPI_OK;
 }
 
@@ -1597,6 +1646,7 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
       rb.map_src = v.cells; rb.map_src_pitch = v.size_x;
       rb.map_valid = true;
       rb.device_stale = true;
+      rb.device_only = false;
       rb.staged_current = false;
     }
   }
@@ -1631,8 +1681,10 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
     const bool single_copy = graphable && plan.fused && h->single_copy;
     // window-only: ship the rows of the costmap the trajectories can plausibly reach instead of the map (the
     // kernel reports a lookup outside them and commits nothing; the attempt is then repeated with the whole map)
+    bool any_device_only = false;
+    for (int r = 0; r < h->R; ++r) {any_device_only = any_device_only || h->robots[r].device_only;}
     const bool window_only = single_copy && h->window_only && !force_resident && h->cfg.iteration_count == 1 &&
-      h->packets_capacity > 0;
+      h->packets_capacity > 0 && !any_device_only;
     h->defer_map_upload = single_copy;
     if (window_only) {
       rc = fill_window_packets(h);

@@ -120,6 +120,8 @@ struct alignas(16) DevCycle
   int32_t track_collisions;
   int32_t need_furthest;                    // some active critic calls setPathFurthestPointIfNotSet
   int32_t need_path_valid;
+  int32_t valid_on_device;                  // the costmap exists only in device memory (mppi_set_costmap_device): the kernels
+                                            // evaluate utils::findPathCosts themselves instead of reading path_valid
   // ---- mutable within the call ----
   int32_t furthest_cached;                  // CriticData::furthest_reached_path_point, -1 = unset
   int32_t fail_flag;                        // CriticData::fail_flag (sticky until prepare())

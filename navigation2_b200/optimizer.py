@@ -149,6 +149,15 @@ class Optimizer(EngineBase):
             float(origin_x), float(origin_y))
         _raise_for(self._lib, self._h, rc)
 
+    def setCostmapDevice(self, device_ptr: int, size_x: int, size_y: int, resolution: float, origin_x: float, origin_y: float,
+                         robot: int = 0, row_pitch: int = 0, producer_stream: int | None = None) -> None:
+        """The costmap where a device-side producer left it (e.g. a torch uint8 tensor's data_ptr() after
+        InflationLayer.updateCostsDevice): device-to-device hand-over, no H2D (mppi_set_costmap_device)."""
+        rc = self._lib.mppi_set_costmap_device(
+            self._h, robot, C.c_void_p(device_ptr), int(size_x), int(size_y), int(row_pitch or size_x), float(resolution),
+            float(origin_x), float(origin_y), C.c_void_p(producer_stream) if producer_stream else None)
+        _raise_for(self._lib, self._h, rc)
+
     def setNoise(self, nvx: np.ndarray, nvy: np.ndarray | None, nwz: np.ndarray, robot: int = 0) -> None:
         """Inject noise tensors, each (T, B) float32 C-contiguous == column-major B x T."""
         fp = C.POINTER(C.c_float)
