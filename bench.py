@@ -474,6 +474,7 @@ def run_ours(args):
         line["roofline_large_batch"] = large_batch_roofline(peak, peak_src, stream, flush)
         line["costmap_inflation"] = inflation_pass(wl, peak, peak_src)
         line["reference_harness"] = reference_harness_section(stream, not args.no_cpu_baseline)
+        line["costmap_device_handoff"] = device_handoff_section(wl)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl)
     if rank == 0:
@@ -519,6 +520,65 @@ def inflation_pass(wl, peak, peak_src):
         layer.close()
         return out
     except Exception as exc:  # the headline line must still be printed
+        return {"error": f"{type(exc).__name__}: {exc}"}
+
+
+def device_handoff_section(wl):
+    """SURVEY.md section 8f row 3 end to end: the costmap never leaves the device.  Per cycle: restore the raw (lethal cells
+    only) map, inflate it on the GPU (k_inflate), hand it to the optimiser device-to-device (mppi_set_costmap_device)
+    and run the control cycle; against the host route on the same handle (inflated map in host memory,
+    mppi_optimize_in_place).  Both loops go through the Python binding, so they carry the same call overhead."""
+    try:
+        import torch
+        from navigation2_b200 import inflation
+        cfg = wl["cfg"]
+        cells = np.asarray(wl["cells"], dtype=np.uint8)
+        raw = np.where(cells == 254, 254, 0).astype(np.uint8)
+        sy, sx = raw.shape
+        layer = inflation.InflationLayer(wl["resolution"], cfg.inscribed_radius, inflation_radius=0.70, cost_scaling_factor=3.0)
+        opt = setup_engine(wl)
+        d_raw = torch.from_numpy(raw).cuda()
+        d_map = torch.empty_like(d_raw)
+        s = torch.cuda.current_stream()
+        n = 300
+
+        def device_cycle():
+            d_map.copy_(d_raw)
+            layer.updateCostsDevice(d_map.data_ptr(), sx, sy, stream=s.cuda_stream)
+            opt.setCostmapDevice(d_map.data_ptr(), sx, sy, wl["resolution"], wl["origin"][0], wl["origin"][1],
+                                 producer_stream=s.cuda_stream)
+            return opt.evalControl(wl["inp"])
+
+        for _ in range(STEADY_STATE_CYCLES):
+            device_cycle()
+        b0 = opt.h2dByteCount()
+        t_dev = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            device_cycle()
+            t_dev.append(time.perf_counter() - t0)
+        h2d_dev = (opt.h2dByteCount() - b0) / n
+        inflated = d_map.cpu().numpy()
+        maps = (inflated, wl["resolution"], wl["origin"][0], wl["origin"][1])
+        for _ in range(STEADY_STATE_CYCLES):
+            opt.evalControl(wl["inp"], costmaps=maps)
+        b0 = opt.h2dByteCount()
+        t_host = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            opt.evalControl(wl["inp"], costmaps=maps)
+            t_host.append(time.perf_counter() - t0)
+        h2d_host = (opt.h2dByteCount() - b0) / n
+        out = {"workload": wl["name"] + "; costmap inflated on the device every cycle",
+               "device_route": {"p50_latency_us": float(np.median(t_dev) * 1e6), "h2d_bytes_per_cycle": int(h2d_dev),
+                                "steps": "D2D restore of the raw map + k_inflate + mppi_set_costmap_device + mppi_optimize"},
+               "host_route": {"p50_latency_us": float(np.median(t_host) * 1e6), "h2d_bytes_per_cycle": int(h2d_host),
+                              "steps": "mppi_optimize_in_place on the already inflated map in host memory (no inflation timed)"},
+               "timed": "time.perf_counter around the Python calls (both routes carry the binding's overhead)"}
+        opt.shutdown()
+        layer.close()
+        return out
+    except Exception as exc:
         return {"error": f"{type(exc).__name__}: {exc}"}
 
 

@@ -33,8 +33,8 @@ NVCC_FLAGS = [
     # no FMA contraction on the device or the host side: bit-identical floats with the CPU oracle
     # on everything that feeds a costmap index
     "-fmad=false",
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall",
-    "-shared",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-fopenmp",
+    "-shared", "-lgomp",
 ]
 
 

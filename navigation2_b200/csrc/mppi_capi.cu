@@ -30,6 +30,12 @@ namespace
 
 thread_local std::string g_create_error;
 
+// fleets of at least this many robots share the per-robot host work of a cycle (Optimizer::prepare, window packing,
+// result unpacking) out over the host cores with OpenMP
+#ifndef MPPI_HOST_PARALLEL_ROBOTS
+#define MPPI_HOST_PARALLEL_ROBOTS 32
+#endif
+
 struct HostRobot
 {
   // Optimizer::last_command_vel_ (doubles of the float command)
@@ -153,6 +159,7 @@ struct MppiHandle
   uint64_t h2d_bytes = 0;         // bytes of costmaps, cycle blocks and window packets copied host -> device so far
   uint64_t window_misses = 0;     // window-only attempts that had to be repeated with the whole map
   bool window_only = true;        // MPPI_B200_NO_WINDOW_ONLY=1: single-launch cycles upload the whole map (A/B measurements)
+  bool window_only_general = true;  // MPPI_B200_NO_WINDOW_GENERAL=1: the general kernels always get whole maps
   uint8_t * h_cycle_block = nullptr;
   size_t cycle_block_bytes = 0;
   uint8_t * h_out = nullptr;
@@ -490,6 +497,7 @@ int allocate(MppiHandle * h)
   }
   if (const char * e = std::getenv("MPPI_B200_NO_SINGLE_COPY"); e && e[0] == '1') {h->single_copy = false;}
   if (const char * e = std::getenv("MPPI_B200_NO_WINDOW_ONLY"); e && e[0] == '1') {h->window_only = false;}
+  if (const char * e = std::getenv("MPPI_B200_NO_WINDOW_GENERAL"); e && e[0] == '1') {h->window_only_general = false;}
   if (const char * e = std::getenv("MPPI_B200_NO_POLL"); e && e[0] == '1') {h->poll_results = false;}
   if (const char * e = std::getenv("MPPI_B200_NO_NOISE_PREFETCH"); e && e[0] == '1') {h->noise_prefetch = false;}
   if (const char * e = std::getenv("MPPI_B200_WINDOW_HALF"); e && std::atoi(e) > 0) {h->window_half_override = std::atoi(e);}
@@ -556,8 +564,9 @@ int ensure_arena(MppiHandle * h, size_t need_stride, int need_path)
   const size_t block = cycle_block_size(h->R, cap);
   if (!same_shape) {
     uint8_t * nh = nullptr, * nd = nullptr;
-    // window packets only where single-launch cycles can happen (all clusters in one wave of the SMs)
-    const size_t packets = h->R <= 148 ? static_cast<size_t>(h->R) * MPPI_MAX_WINDOW_BYTES : 0;
+    // window packets: room for every robot's largest window (single-launch cycles and the general kernels both take
+    // window-only uploads)
+    const size_t packets = static_cast<size_t>(h->R) * MPPI_MAX_WINDOW_BYTES;
     const size_t total = stride * h->R + block + packets;
     CU_CHECK(h, cudaMallocHost(&nh, total));
     std::memset(nh, 0, total);
@@ -1132,13 +1141,21 @@ int fill_window_packets(MppiHandle * h)
 {
   size_t off = 0;
   for (int r = 0; r < h->R; ++r) {
-    HostRobot & rb = h->robots[r];
     DevCycle & cy = *h->hcyc(r);
     cy.win_packet_off = static_cast<uint32_t>(off);
     if (!cy.run || cy.win_w <= 0 || cy.win_h <= 0) {continue;}
     const size_t bytes = static_cast<size_t>(cy.win_w) * cy.win_h;
     if (off + bytes > h->packets_capacity) {h->error = "window packets overflow"; return MPPI_ERR_UNSUPPORTED;}
-    uint8_t * dst = h->h_packets + off;
+    off += bytes;
+  }
+  h->packets_used = off;
+  // the rows of every robot's window, packed; robots are independent (a fleet's packing is shared out over the host cores)
+#pragma omp parallel for schedule(static) if (h->R >= MPPI_HOST_PARALLEL_ROBOTS)
+  for (int r = 0; r < h->R; ++r) {
+    const HostRobot & rb = h->robots[r];
+    const DevCycle & cy = *h->hcyc(r);
+    if (!cy.run || cy.win_w <= 0 || cy.win_h <= 0) {continue;}
+    uint8_t * dst = h->h_packets + cy.win_packet_off;
     // the window's right edge is rounded up to 16 cells and may run past size_x into the row padding
     const int copy_w = std::min<int>(cy.win_w, static_cast<int>(rb.size_x) - cy.win_x0);
     for (int row = 0; row < cy.win_h; ++row) {
@@ -1146,9 +1163,7 @@ int fill_window_packets(MppiHandle * h)
       std::memcpy(dst + static_cast<size_t>(row) * cy.win_w, src, copy_w);
       if (copy_w < cy.win_w) {std::memset(dst + static_cast<size_t>(row) * cy.win_w + copy_w, 0, cy.win_w - copy_w);}
     }
-    off += bytes;
   }
-  h->packets_used = off;
   return MPPI_OK;
 }
 
@@ -1650,11 +1665,19 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
       rb.staged_current = false;
     }
   }
-  for (int r = 0; r < h->R; ++r) {
-    out[r].retries = 0;
-    out[r].status = MPPI_OK;
-    rc = prepare_robot(h, r, in[r], -1, false);
-    if (rc != MPPI_OK) {return rc;}
+  {
+    int prc = MPPI_OK;
+#pragma omp parallel for schedule(static) if (h->R >= MPPI_HOST_PARALLEL_ROBOTS)
+    for (int r = 0; r < h->R; ++r) {
+      out[r].retries = 0;
+      out[r].status = MPPI_OK;
+      const int one = prepare_robot(h, r, in[r], -1, false);   // writes only robot r's slots of the cycle block
+      if (one != MPPI_OK) {
+#pragma omp critical
+        prc = one;
+      }
+    }
+    if (prc != MPPI_OK) {return prc;}
   }
   tick(1, tp);
   const LaunchPlan plan = make_plan(h);
@@ -1671,6 +1694,7 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
     };
   bool first = true;
   bool force_resident = false;  // a window-only attempt missed: same attempt again with the whole map
+  std::vector<char> parked(h->R, 0);
   while (true) {
     // One attempt = H2D of the cycle block, the optimize() iterations, D2H of the result block.  The
     // common case (first attempt, own stream, no per-kernel timing) replays a captured CUDA graph:
@@ -1683,8 +1707,14 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
     // kernel reports a lookup outside them and commits nothing; the attempt is then repeated with the whole map)
     bool any_device_only = false;
     for (int r = 0; r < h->R; ++r) {any_device_only = any_device_only || h->robots[r].device_only;}
-    const bool window_only = single_copy && h->window_only && !force_resident && h->cfg.iteration_count == 1 &&
-      h->packets_capacity > 0 && !any_device_only;
+    bool host_maps = true;   // every robot's cells are readable on the host (staging slab or the caller's buffer)
+    for (int r = 0; r < h->R; ++r) {host_maps = host_maps && h->robots[r].map_src != nullptr;}
+    // The general kernels take window-only uploads too (kernel A stages the packed rows, the finalize kernel's
+    // validator reads them, a lookup outside raises the robot's RED_MAP_MISS word and nothing is committed): a
+    // fleet cycle then moves ~9 KB per robot instead of staging and uploading 40 KB maps.
+    const bool window_general = graphable && !plan.fused && h->window_only_general && views != nullptr;
+    const bool window_only = (single_copy || window_general) && h->window_only && !force_resident &&
+      h->cfg.iteration_count == 1 && h->packets_capacity > 0 && !any_device_only && host_maps && h->cfg.shard_world == 1;
     h->defer_map_upload = single_copy;
     if (window_only) {
       rc = fill_window_packets(h);
@@ -1739,7 +1769,7 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
         if (h->graphs.size() >= 16) {drop_graphs(h);}
         h->graphs.push_back({key, exec});
       }
-      if (!single_copy) {
+      if (!single_copy && !window_only) {
         rc = upload_cycle_block(h, h->stream);
         if (rc != MPPI_OK) {return rc;}
       }
@@ -1799,28 +1829,35 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
     }
     if (!stamped) {CU_CHECK(h, cudaStreamSynchronize(h->stream));}
     tick(4, tp);
-    if (window_only) {
-      bool missed = false;
-      for (int r = 0; r < h->R; ++r) {
-        const DevOutHeader * hdr = reinterpret_cast<const DevOutHeader *>(h->h_out + static_cast<size_t>(r) * h->out_stride);
-        missed = missed || (h->hcyc(r)->run && hdr->map_miss);
-      }
-      if (missed) {
-        h->window_misses++;
-        force_resident = true;
-        first = true;   // nothing was committed: this is still the first attempt
+    // A window-only attempt may have missed for SOME robots of a fleet (a lookup outside the uploaded window: that
+    // robot committed nothing).  The others are finished now — their results stand, they are not run again — and
+    // the missed ones repeat the same attempt with the whole map.  Robots whose fallback() asks for another attempt
+    // are parked until no fresh rerun is pending (a fresh rerun starts from zero costs, a retry accumulates,
+    // optimizer.cpp:281-298 / :335).
+    bool any_missed = false, any_retry = false;
+    for (int r = 0; r < h->R; ++r) {
+      if (!h->hcyc(r)->run) {continue;}  // finished in an earlier attempt, or parked
+      const DevOutHeader * hdr = reinterpret_cast<const DevOutHeader *>(h->h_out + static_cast<size_t>(r) * h->out_stride);
+      if (window_only && hdr->map_miss) {
+        any_missed = true;
+        if (std::getenv("MPPI_B200_DEBUG_MISS")) {std::fprintf(stderr, "[mppi] window miss: robot %d seq %u\n", r, h->cycle_seq);}
         continue;
       }
-    }
-    bool any_retry = false;
-    for (int r = 0; r < h->R; ++r) {
-      if (!h->hcyc(r)->run) {continue;}  // finished in an earlier attempt
       bool retry = false;
       rc = finish_attempt(h, r, out[r], retry);
       if (rc != MPPI_OK) {return rc;}
-      any_retry = any_retry || retry;
+      if (retry) {parked[r] = 1; h->hcyc(r)->run = 0;}
     }
     tick(5, tp);
+    if (any_missed) {
+      h->window_misses++;
+      force_resident = true;
+      first = true;   // nothing was committed for the robots still running: this is still their first attempt
+      continue;
+    }
+    for (int r = 0; r < h->R; ++r) {
+      if (parked[r]) {parked[r] = 0; h->hcyc(r)->run = 1; any_retry = true;}
+    }
     if (!any_retry) {break;}
   }
   h->ht_n++;

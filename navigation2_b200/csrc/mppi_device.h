@@ -35,6 +35,7 @@ enum
   RED_OBS_FREE = 3,    // same for ObstaclesCritic
   MPPI_AR1_WORDS = 4,
   RED_COST_MIN = 4,    // min total cost over the local rows, ~ordered(float)
+  RED_MAP_MISS = 5,    // general kernels, window-only cycle: some lookup fell outside the uploaded costmap window
   RED_WORDS = 8
 };
 

@@ -187,3 +187,40 @@ def test_non_shift_mode_controller_period_below_model_dt(batch, full):
         pair.close()
     else:
         _lean_pair_check(cfg, cells, path, (10.0, 10.0, 0.0), (0.25, 0.0, 0.1), 6, f"non-shift-lean-B{batch}")
+
+
+@pytest.mark.parametrize("R,batch", [(3, 1000), (20, 2000)])
+def test_fleet_window_miss_reruns_only_the_robots_that_missed(R, batch):
+    """Window-only uploads for fleets, single-launch kernel (3 robots) and general kernels (20 robots): with a window
+    forced down to 0.15 m around the robot some robots look up cells outside it and repeat the cycle with the whole
+    map, the others keep their first result (running them twice would shift their control sequence twice).  Every
+    robot must end every cycle exactly where a handle with the regular window ends it."""
+    import os
+    cfg = P.nav2_bringup_config(n_robots=R, batch_size=batch)
+    regular = nb.Optimizer(cfg)
+    os.environ["MPPI_B200_WINDOW_HALF"] = "3"
+    try:
+        tiny = nb.Optimizer(cfg)
+    finally:
+        os.environ.pop("MPPI_B200_WINDOW_HALF")
+    maps, inputs = [], []
+    for r in range(R):
+        cells = build_map("blocks", seed=300 + r, size=200, pose=(5.0, 5.0), n_blocks=12)
+        maps.append((cells, 0.05, 0.0, 0.0))
+        nvx, nvy, nwz = S.seeded_noise(batch, 56, (cfg.vx_std, cfg.vy_std, cfg.wz_std), seed=900 + r)
+        if r % 3 == 0:
+            nvx = nvx * 0.0          # these robots barely move: they stay inside even the tiny window
+        for eng in (regular, tiny):
+            eng.setNoise(nvx, nvy, nwz, robot=r)
+        path = S.arc_path((5.0, 5.0, 0.3 * r), n_points=80, curvature=0.05)
+        inputs.append(nb.CycleInput(pose=(5.0, 5.0, 0.3 * r), speed=(0.0 if r % 3 == 0 else 0.3, 0.0, 0.0), path=path,
+                                    goal=tuple(path[-1]), goal_checker_xy_tolerance=0.25))
+    for cycle in range(4):
+        a = regular.evalControl(inputs, costmaps=maps)
+        b = tiny.evalControl(inputs, costmaps=maps)
+        for r in range(R):
+            np.testing.assert_array_equal(a[r].control_sequence, b[r].control_sequence, err_msg=f"robot {r} cycle {cycle}")
+            assert a[r].cmd == b[r].cmd
+    assert regular.windowMissCount() == 0
+    assert tiny.windowMissCount() >= 3
+    regular.shutdown(); tiny.shutdown()
