@@ -400,8 +400,14 @@ def run_ours(args):
         torch.cuda.synchronize()
         return t, (opt.h2dByteCount() - b0) / args.steps
 
+    # the e2e loops start from a device and a host that have been running control cycles for a while (clocks, caches,
+    # page tables settled): a controller runs continuously, the first ~100 calls after a pause are 15 % slower
+    t_settle = time.perf_counter()
+    while time.perf_counter() - t_settle < 0.3:
+        opt.timeE2E(wl["cells"], wl["resolution"], wl["origin"], inputs, 50, in_place=True)
     two_call_times, two_call_h2d = timed_e2e(False)
     e2e_times, h2d = timed_e2e(True)
+    e2e_status = getattr(opt, "last_timed_status", None)
     e2e_total = float(e2e_times.sum())
     py_times = []
     maps = [(wl["cells"], wl["resolution"], wl["origin"][0], wl["origin"][1])] * R
@@ -453,6 +459,8 @@ def run_ours(args):
                 "timed": "mppi_time_e2e: steady_clock around mppi_optimize_in_place (costmap read in the caller's memory) "
                          "inside the C library",
                 "window_misses": int(window_misses),
+                "last_cycle_status_and_retries": e2e_status,
+                "settle": "0.3 s of untimed control cycles before the e2e loops",
                 "two_call": {"p50_latency_us": float(np.median(two_call_times) * 1e6), "h2d_bytes_per_step": int(two_call_h2d),
                              "timed": "mppi_upload_costmap (whole map staged) + mppi_optimize"},
                 "p50_latency_us_python_binding": float(np.median(py_times) * 1e6)},

@@ -172,6 +172,8 @@ struct MppiHandle
   uint64_t fused_checked_key = ~0ull;
   bool fused_checked_ok = false;
   bool have_cycle = false;     // a cycle block is resident (mppi_enqueue_resident allowed)
+  struct LaunchPlanBox * resident_plan = nullptr;  // the launch plan of the captured cycle (the host cycle block's run flags are
+                                                   // cleared when a cycle finishes: a plan made afterwards would see no active critic)
   bool resident_capture = false;  // keep pristine copies of the cycle inputs for mppi_enqueue_resident
   bool use_graphs = true;      // MPPI_B200_NO_GRAPH=1 launches node by node
   struct CycleGraph {uint64_t key; cudaGraphExec_t exec;};
@@ -733,6 +735,14 @@ int prepare_robot(MppiHandle * h, int r, const MppiCycleIn & in, int preset_furt
   cy.origin_y_f = static_cast<float>(rb.origin_y);
   cy.resolution_f = static_cast<float>(rb.resolution);
   cy.size_x = rb.size_x; cy.size_y = rb.size_y; cy.pitch = rb.pitch;
+  {
+    // Bound on |float estimate - double quotient| of Costmap2D::worldToMap for points on this map (kernel A's
+    // obstacle_cell): the float origin and resolution are off by <= 2^-24 relative, the float subtraction and division
+    // round once each; in cells that is < 2^-24 (|origin| / res + 4 size).  Four times that, plus a floor.
+    const double cells = std::max(std::fabs(rb.origin_x), std::fabs(rb.origin_y)) / rb.resolution + 4.0 * std::max(rb.size_x, rb.size_y);
+    const double eps = std::ldexp(cells, -22) + 1e-6;
+    cy.w2m_eps = eps < 0.2 ? static_cast<float>(eps) : 2.0f;
+  }
 
   // utils::findPathCosts (tools/utils.hpp:358-387): validity of path points 0 .. n-2
   uint8_t * valid = h->hvalid(r);
@@ -901,6 +911,11 @@ struct LaunchPlan
   int cluster_size;
 };
 
+}  // namespace
+struct LaunchPlanBox {LaunchPlan plan;};
+namespace
+{
+
 LaunchPlan make_plan(MppiHandle * h)
 {
   LaunchPlan p{};
@@ -914,7 +929,9 @@ LaunchPlan make_plan(MppiHandle * h)
   }
   p.path_cap = std::max(max_n, 1);
   // small batches: narrower blocks spread the trajectories over more SMs (latency-bound regime)
-  p.block_a = (static_cast<size_t>(h->B) * h->R <= 148u * 64u) ? 64 : MPPI_BLOCK_A;
+  // (up to four 64-thread blocks per SM before switching to 256-thread blocks: 16384 trajectories are 256 small blocks
+  // on all 148 SMs instead of 64 large ones on 64 of them)
+  p.block_a = (static_cast<size_t>(h->B) * h->R <= 148u * 64u * 4u) ? 64 : MPPI_BLOCK_A;
   const int lag = std::max({std::max(h->off_vx, 1) - 1, std::max(h->off_wz, 1) - 1,
         h->holo ? std::max(h->off_vy, 1) - 1 : 0});
   const int ring = lag > 0 ? lag + 1 : 0;
@@ -1362,6 +1379,7 @@ int mppi_destroy(MppiHandle * h)
   if (h->d_xstate) {cudaFree(h->d_xstate);}
   if (h->h_xerror) {cudaFreeHost(h->h_xerror);}
   if (h->d_flush) {cudaFree(h->d_flush);}
+  delete h->resident_plan;
   for (auto & rb : h->robots) {if (rb.stage_event) {cudaEventDestroy(rb.stage_event);}}
   cudaEventDestroy(h->map_event);
   if (h->noise_event) {cudaEventDestroy(h->noise_event);}
@@ -1781,6 +1799,8 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
       if (rc != MPPI_OK) {return rc;}
       if (first) {
         if (h->resident_capture) {
+          if (!h->resident_plan) {h->resident_plan = new LaunchPlanBox();}
+          h->resident_plan->plan = plan;
           // pristine copies for mppi_enqueue_resident
           CU_CHECK(h, cudaMemcpyAsync(h->d_cycle_saved, h->d_cycle_block, h->cycle_block_bytes, cudaMemcpyDeviceToDevice, h->stream));
           CU_CHECK(h, cudaMemcpyAsync(h->d_u_saved, h->d_u, sizeof(float) * 3 * h->T * h->R, cudaMemcpyDeviceToDevice, h->stream));
@@ -2130,8 +2150,8 @@ int mppi_enqueue_resident(MppiHandle * h, void * cuda_stream)
   // optimize() kernels and nothing else: no restore copies, no memset.
   int rc = wait_map(h, s);
   if (rc != MPPI_OK) {return rc;}
-  const LaunchPlan plan = make_plan(h);
-  return enqueue_iterations(h, s, plan, true, CycleSource::PRISTINE);
+  if (!h->resident_plan) {h->error = "no captured cycle"; return MPPI_ERR_NOT_READY;}
+  return enqueue_iterations(h, s, h->resident_plan->plan, true, CycleSource::PRISTINE);
 }
 
 // `steps` resident replays on the handle's stream, each bracketed by CUDA events, after `warmup` untimed ones.
@@ -2180,7 +2200,7 @@ int mppi_enqueue_score_resident(MppiHandle * h, void * cuda_stream)
   if (int wrc = wait_map(h, s); wrc != MPPI_OK) {return wrc;}
   CU_CHECK(h, cudaMemcpyAsync(h->d_cycle_block, h->d_cycle_saved, h->cycle_block_bytes, cudaMemcpyDeviceToDevice, s));
   CU_CHECK(h, cudaMemsetAsync(h->d_costs, 0, sizeof(float) * h->B * h->R, s));
-  const LaunchPlan plan = make_plan(h);
+  const LaunchPlan plan = h->resident_plan ? h->resident_plan->plan : make_plan(h);
   KArgs a = make_args(h);
   a.materialize = 0;
   KPlanA ka = plan.ka;

@@ -123,6 +123,8 @@ struct alignas(16) DevCycle
   int32_t need_path_valid;
   int32_t valid_on_device;                  // the costmap exists only in device memory (mppi_set_costmap_device): the kernels
                                             // evaluate utils::findPathCosts themselves instead of reading path_valid
+  float w2m_eps;                            // how far (in cells) the float estimate of the double world -> map quotient can be off
+                                            // for this robot's map (>= 1: the estimate is never trusted); see obstacle_cell()
   // ---- mutable within the call ----
   int32_t furthest_cached;                  // CriticData::furthest_reached_path_point, -1 = unset
   int32_t fail_flag;                        // CriticData::fail_flag (sticky until prepare())

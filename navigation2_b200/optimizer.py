@@ -331,6 +331,7 @@ class Optimizer(EngineBase):
             float(origin[0]), float(origin[1]), c_in, c_out, int(cycles), 1 if in_place else 0,
             t.ctypes.data_as(C.POINTER(C.c_double)))
         _raise_for(self._lib, self._h, rc)
+        self.last_timed_status = [(int(c_out[r].status), int(c_out[r].retries)) for r in range(self.R)]
         return t
 
     def timeE2EViews(self, costmaps, inputs, cycles: int) -> np.ndarray:
@@ -351,6 +352,7 @@ class Optimizer(EngineBase):
         t = np.zeros(cycles, dtype=np.float64)
         rc = self._lib.mppi_time_e2e_views(self._h, views, c_in, c_out, int(cycles), t.ctypes.data_as(C.POINTER(C.c_double)))
         _raise_for(self._lib, self._h, rc)
+        self.last_timed_status = [(int(c_out[r].status), int(c_out[r].retries)) for r in range(self.R)]
         return t
 
     def enqueueResident(self, cuda_stream: int | None = None) -> None:

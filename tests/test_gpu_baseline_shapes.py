@@ -165,6 +165,7 @@ def test_c5_fleet_general_path_each_robot_against_its_own_oracle():
                 eng.setState(cpus[r].getState(), robot=r)
                 eng.setControlSequence(cpus[r].getOptimalControlSequence(), robot=r)
     assert fleet.launchCount() - l0 == 3 * 4, "the fleet must run the general four-kernel path"
+    assert fleet_in_place.windowMissCount() == 0, "every lookup of these robots lies inside the uploaded window"
     for e in [fleet, fleet_in_place] + cpus:
         e.shutdown()
 

@@ -586,3 +586,30 @@ def test_measurement_entry_points():
     assert hot.shape == (20,) and np.all(hot > 0.005) and np.all(hot < 5.0)
     assert np.median(cold) > np.median(hot)
     opt.shutdown()
+
+
+@pytest.mark.parametrize("model", ["omni", "diff_drive"])
+def test_resident_replay_recomputes_the_captured_cycle(model):
+    """mppi_enqueue_resident (what bench.py's `value` times) must run the SAME kernels on the same inputs as the live
+    cycle it captured: identical per-trajectory costs, with every critic of the list active (a replay planned from the
+    finished cycle's cleared run flags once picked an instantiation without ObstaclesCritic)."""
+    cfg = P.make_config({"batch_size": 12000, "time_steps": 60, "motion_model": model, "controller_frequency": 20.0},
+                        ALL_CRITICS, {"VelocityDeadbandCritic": {"deadband_velocities": [0.05, 0.05, 0.05]}}, robot_radius=0.22,
+                        inflation={"cost_scaling_factor": 3.0, "inflation_radius": 0.70})
+    opt = nb.Optimizer(cfg)
+    cells = build_map("blocks", seed=3, inscribed=cfg.inscribed_radius, n_blocks=40, clear_radius=0.6)
+    opt.setCostmap(cells, 0.05, 0.0, 0.0)
+    path = S.arc_path((10.0, 10.0, 0.3), n_points=120, curvature=-0.2)
+    inp = nb.CycleInput(pose=(10.0, 10.0, 0.3), speed=(0.2, 0.0, 0.0), path=path, goal_checker_xy_tolerance=0.25)
+    for _ in range(6):
+        opt.evalControl(inp)
+    opt.setResidentCapture(True)
+    opt.evalControl(inp)
+    live = opt.getTensor(capi.TENSOR_COSTS)
+    for _ in range(2):
+        opt.enqueueResident(None)
+        opt.synchronize()
+        replay = opt.getTensor(capi.TENSOR_COSTS)
+        assert np.isfinite(replay).all()
+        np.testing.assert_array_equal(replay, live)
+    opt.shutdown()
