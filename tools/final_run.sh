@@ -7,8 +7,8 @@ python bench.py > gpurun_out/r01_plain_bench.json 2> gpurun_out/r01_plain_bench.
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/final_ref_n1.json 2> gpurun_out/final_ref_n1.err; echo ref rc=$?
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches_bench.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r01_ncu_bench.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_fused_cluster -c 2 --launch-skip 4 -f -o gpurun_out/r01_fused_c1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-large-batch > gpurun_out/r01_ncu_fused.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_rollout_score|k_softmax_partial|k_path_score|k_finalize' -c 4 --launch-skip 8 -f -o gpurun_out/r01_kernels_c4 python tests/run_large_batch.py 2 > gpurun_out/r01_ncu_c4.log 2>&1
-python tests/run_inflation_bench.py > gpurun_out/r01_inflation_bench.json 2> gpurun_out/r01_inflation_bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 50 --csv --log-file gpurun_out/r01_launches_inflation.csv python tests/run_inflation_profile.py > gpurun_out/r01_ncu_inflation_list.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_inflate -f -o gpurun_out/r01_inflate python tests/run_inflation_profile.py > gpurun_out/r01_ncu_inflate.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_rollout_score|k_softmax_partial|k_path_score|k_finalize' -c 4 --launch-skip 8 -f -o gpurun_out/r01_kernels_c4 python tools/large_batch.py 2 > gpurun_out/r01_ncu_c4.log 2>&1
+python tools/inflation_bench.py > gpurun_out/r01_inflation_bench.json 2> gpurun_out/r01_inflation_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 50 --csv --log-file gpurun_out/r01_launches_inflation.csv python tools/inflation_profile.py > gpurun_out/r01_ncu_inflation_list.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_inflate -f -o gpurun_out/r01_inflate python tools/inflation_profile.py > gpurun_out/r01_ncu_inflate.log 2>&1
 ls -la gpurun_out | tail -15

@@ -7,9 +7,10 @@ import bench
 from navigation2_b200 import capi
 wl = bench.workload_c1()
 opt = bench.setup_engine(wl)
-for _ in range(5):
+maps = (wl["cells"], wl["resolution"], wl["origin"][0], wl["origin"][1])
+for _ in range(int(os.environ.get("PHASE_CLOCK_CYCLES", "15"))):
     try:
-        opt.evalControl(wl["inp"])
+        opt.evalControl(wl["inp"], costmaps=maps)
     except Exception as e:      # experiments that corrupt results on purpose still leave the clocks
         print("evalControl:", type(e).__name__)
 out = np.zeros(16 * 16 * 32, dtype=np.int64)
