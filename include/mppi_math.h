@@ -89,10 +89,34 @@ MPPI_HD void mppi_sincosf(float x, float * s_out, float * c_out)
 }
 
 /* utils.hpp:254-262 normalize_angles (float, Eigen side): fmodf is exact on CPU and GPU. */
+/* fmodf(x, m) for m > 0 without the library's division loop when |x| < 2m, which is every angle this code meets:
+ * fmod is exact and keeps the dividend's sign, so it is x itself for |x| < m and x -/+ m for m <= |x| < 2m — and that
+ * difference is exactly representable (Sterbenz: m <= |x| <= 2m), so the float subtraction returns the same bits. */
+MPPI_HD float mppi_fmodf_small(float x, float m)
+{
+  const float ax = fabsf(x);
+  if (ax < m) {return x;}
+  if (ax < 2.0f * m) {
+    const float r = x < 0.0f ? x + m : x - m;
+    return r == 0.0f ? copysignf(0.0f, x) : r;   /* fmod(-m, m) is -0 */
+  }
+  return fmodf(x, m);
+}
+MPPI_HD double mppi_fmod_small(double x, double m)
+{
+  const double ax = fabs(x);
+  if (ax < m) {return x;}
+  if (ax < 2.0 * m) {
+    const double r = x < 0.0 ? x + m : x - m;
+    return r == 0.0 ? copysign(0.0, x) : r;
+  }
+  return fmod(x, m);
+}
+
 MPPI_HD float mppi_normalize_anglef(float angle)
 {
   const float x = angle + MPPI_PIF;
-  const float rem = fmodf(x, 2.0f * MPPI_PIF);
+  const float rem = mppi_fmodf_small(x, 2.0f * MPPI_PIF);
   return rem < 0.0f ? rem + MPPI_PIF : rem - MPPI_PIF;
 }
 
@@ -109,7 +133,7 @@ MPPI_HD float mppi_shortest_angular_distancef(float from, float to)
  */
 MPPI_HD double mppi_angles_normalize_angle(double angle)
 {
-  const double result = fmod(angle + M_PI, 2.0 * M_PI);
+  const double result = mppi_fmod_small(angle + M_PI, 2.0 * M_PI);
   if (result <= 0.0) {return result + M_PI;}
   return result - M_PI;
 }

@@ -997,7 +997,7 @@ LaunchPlan make_plan(MppiHandle * h)
     // the fused kernel copies the path arrays 16 bytes at a time: capacity rounded up to 16 points (max_path is a
     // power of two >= 256, the cycle block is zero-initialised, entries past n_path are never read as path points)
     const int fused_cap = std::min(h->max_path, (p.path_cap + 15) & ~15);
-    p.sm_f = mppi_smem_layout_f(h->T, h->holo, fused_cap, static_cast<int>(h->cfg.n_critics) + 3, obstacles, win_bytes);
+    p.sm_f = mppi_smem_layout_f(h->T, h->holo, fused_cap, static_cast<int>(h->cfg.n_critics) + 3, obstacles, win_bytes, h->n_pa);
     if (p.sm_f.total <= 227u * 1024u) {
       const uint64_t key = (static_cast<uint64_t>(p.sm_f.total) << 8) | static_cast<uint64_t>(cs);
       if (h->fused_checked_key != key) {

@@ -41,13 +41,14 @@ struct KSmemF
   uint32_t off_xch;    // FusedExchange + float W[3][T]: read by the other CTAs through DSMEM
   uint32_t off_lut;    // float obstacle distance LUT [2][256]
   uint32_t off_fin;    // finalize scratch, 11 T floats
+  uint32_t off_pa;     // PathAlign scratch [2][n_pa][MPPI_FUSED_G] (n_pa <= T / 4 + 1 at the smallest sampling step the fused path takes)
   uint32_t off_win;    // uint8 costmap window
   int32_t path_cap;
   int32_t has_lut;   // the obstacle LUT is allocated (ObstaclesCritic configured)
   uint32_t total;
 };
 
-KSmemF mppi_smem_layout_f(int T, bool holo, int path_cap, int n_terms, bool obstacles, int win_bytes);
+KSmemF mppi_smem_layout_f(int T, bool holo, int path_cap, int n_terms, bool obstacles, int win_bytes, int n_pa);
 cudaError_t mppi_launch_fused(const KArgs & a, const KSmemF & sm, bool holo, int cluster_size, cudaStream_t stream);
 bool mppi_fused_supported(const KSmemF & sm, bool holo, int cluster_size);
 

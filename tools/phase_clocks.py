@@ -56,3 +56,7 @@ w0 = clk[:, 1, 30]; w1 = clk[:, 1, 31]
 print("WALL kernel entry spread over ranks (ns):", int(w0.max() - w0.min()), " rank0 in-kernel ns:", int(w1[0] - w0[0]),
       " other ranks in-kernel ns:", [int(b - a) for a, b in zip(w0[1:], w1[1:])][:5], " first entry -> last exit ns:", int(w1.max() - w0.min()))
 print("WALL rank0 cycles:", int(clk[0, 0, 14] - clk[0, 0, 0]), "=> effective MHz:", (clk[0, 0, 14] - clk[0, 0, 0]) / max(1, (w1[0] - w0[0])) * 1e3)
+
+print("P5 detail, rank 1 per warp (cycles since kernel start): start of P5 (slot 8), after the PathAlign pre-pass (22), after the critic loop (23), before the copy wait (24), end (9)")
+for slot in (8, 22, 23, 24, 9):
+    print(f"  slot {slot:2d}:", [int(v - t0) if v else 0 for v in clk[1, :, slot]])
