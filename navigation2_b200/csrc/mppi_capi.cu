@@ -127,7 +127,7 @@ struct MppiHandle
   size_t map_stride = 0;
   DevStatic * d_static = nullptr;
   uint8_t * d_cycle_block = nullptr, * d_cycle_saved = nullptr;   // [DevCycle R][path R*4*max_path f32][valid R*max_path]
-  uint8_t * d_out = nullptr;
+  uint2 * d_out_tag = nullptr;    // device alias of h_out_tag
   size_t out_stride = 0;
   int n_partial_blocks = 1;
   int max_path = 0;
@@ -162,7 +162,8 @@ struct MppiHandle
   bool window_only_general = true;  // MPPI_B200_NO_WINDOW_GENERAL=1: the general kernels always get whole maps
   uint8_t * h_cycle_block = nullptr;
   size_t cycle_block_bytes = 0;
-  uint8_t * h_out = nullptr;
+  uint8_t * h_out = nullptr;      // plain result blocks [R][out_stride], filled by unpack_results from h_out_tag
+  uint2 * h_out_tag = nullptr;    // mapped pinned: what the kernels write ([R][out_stride / 4] tagged words, KArgs::out_tag)
   uint8_t * h_map_stage = nullptr;
 
   bool host_timers = false;    // MPPI_B200_HOST_TIMERS=1: accumulate host-side phase times, printed by mppi_destroy
@@ -212,9 +213,10 @@ void free_device(MppiHandle * h)
   F(h->d_obs_rep); F(h->d_last); F(h->d_pa); F(h->d_costs); F(h->d_softmax); F(h->d_critic_costs);
   F(h->d_collisions); F(h->d_dbg_cost); F(h->d_dbg_obs); F(h->d_red); F(h->d_partials); F(h->d_slot);
   F(h->d_vis_xy); F(h->d_phase_clocks); F(h->d_slot_all); F(h->d_static); F(h->d_cycle_saved);
-  h->d_out = nullptr;  // alias of the mapped h_out
+  h->d_out_tag = nullptr;  // alias of the mapped h_out_tag
   // the arena (costmaps + cycle block) outlives a reconfiguration: mppi_destroy frees it
-  if (h->h_out) {cudaFreeHost(h->h_out); h->h_out = nullptr;}
+  if (h->h_out_tag) {cudaFreeHost(h->h_out_tag); h->h_out_tag = nullptr;}
+  std::free(h->h_out); h->h_out = nullptr;
 }
 
 // MotionModel::offsetSteps (motion_models.hpp:221-227) and predict's own rounding (:160-162)
@@ -532,11 +534,14 @@ int allocate(MppiHandle * h)
   CU_CHECK(h, cudaMemcpy(h->d_static, &h->h_static, sizeof(DevStatic), cudaMemcpyHostToDevice));
   if (h->max_path < 256) {h->max_path = 256;}
   h->out_stride = (sizeof(DevOutHeader) + 6 * T * sizeof(float) + 15) & ~static_cast<size_t>(15);
-  // result blocks live in mapped pinned host memory: the finalize kernel's ~1.4 KB per robot goes straight over
-  // PCIe as posted writes and is visible to the host after the stream synchronises (no D2H copy node)
-  CU_CHECK(h, cudaHostAlloc(&h->h_out, R * h->out_stride, cudaHostAllocMapped));
-  std::memset(h->h_out, 0, R * h->out_stride);
-  CU_CHECK(h, cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->d_out), h->h_out, 0));
+  // result blocks live in mapped pinned host memory: the finalize kernel's ~350 words per robot go straight over
+  // PCIe as posted 8-byte writes, each carrying the cycle's sequence number (KArgs::out_tag): no D2H copy node, no
+  // fence in the kernel.  unpack_results() moves a finished block into the plain layout the host code reads.
+  CU_CHECK(h, cudaHostAlloc(&h->h_out_tag, R * (h->out_stride / 4) * sizeof(uint2), cudaHostAllocMapped));
+  std::memset(h->h_out_tag, 0, R * (h->out_stride / 4) * sizeof(uint2));
+  CU_CHECK(h, cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->d_out_tag), h->h_out_tag, 0));
+  h->h_out = static_cast<uint8_t *>(std::calloc(R, h->out_stride));
+  if (!h->h_out) {h->error = "out of host memory"; return MPPI_ERR_CUDA;}
   return MPPI_OK;
 }
 
@@ -894,7 +899,11 @@ KArgs make_args(MppiHandle * h)
   a.cyc_in = a.cyc; a.u_in = a.u; a.hist_in = a.ctrl_hist;
   a.st = h->d_static;
   a.phase_clocks = h->d_phase_clocks;
-  a.out = h->d_out; a.out_stride = h->out_stride;
+  a.out_tag = h->d_out_tag; a.out_words = h->out_stride / 4;
+  {
+    static const int dbg = [] {const char * e = std::getenv("MPPI_B200_DEBUG_FLAGS"); return e ? std::atoi(e) : 0;}();
+    a.debug_flags = dbg; a.pad_debug = 0;
+  }
   return a;
 }
 
@@ -1227,6 +1236,40 @@ int wait_map(MppiHandle * h, cudaStream_t stream)
     h->map_event_pending = false;
   }
   return MPPI_OK;
+}
+
+// Robot r's result block as the kernels publish it (KArgs::out_tag): 8-byte words, value in the low half, the
+// sequence number of the cycle that wrote it in the high half.
+static inline const volatile uint64_t * tagged_block(const MppiHandle * h, int r)
+{
+  return reinterpret_cast<const volatile uint64_t *>(h->h_out_tag) + static_cast<size_t>(r) * (h->out_stride / 4);
+}
+
+// True once every word of robot r's result block carries `seq`: the header first (a window miss publishes nothing
+// else), then the control sequence and the optimal trajectory.
+static bool results_complete(const MppiHandle * h, int r, uint32_t seq)
+{
+  const volatile uint64_t * w = tagged_block(h, r);
+  constexpr int HW = static_cast<int>(sizeof(DevOutHeader) / 4);
+  for (int i = 0; i < HW; ++i) {
+    if (static_cast<uint32_t>(w[i] >> 32) != seq) {return false;}
+  }
+  if (static_cast<uint32_t>(w[offsetof(DevOutHeader, map_miss) / 4]) != 0u) {return true;}
+  const int n = HW + 6 * h->T;
+  for (int i = HW; i < n; ++i) {
+    if (static_cast<uint32_t>(w[i] >> 32) != seq) {return false;}
+  }
+  return true;
+}
+
+// Moves robot r's published words into the plain block (h_out: DevOutHeader, control sequence, optimal trajectory)
+// that the rest of the host code reads.
+static void unpack_results(MppiHandle * h, int r)
+{
+  const volatile uint64_t * w = tagged_block(h, r);
+  uint32_t * dst = reinterpret_cast<uint32_t *>(h->h_out + static_cast<size_t>(r) * h->out_stride);
+  const size_t n = h->out_stride / 4;
+  for (size_t i = 0; i < n; ++i) {dst[i] = static_cast<uint32_t>(w[i]);}
 }
 
 // fallback() (optimizer.cpp:281-298) + the tail of evalControl (:261-269) for one robot after an
@@ -1828,10 +1871,11 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
       h->noise_prefetched = true;
     }
     tick(3, tp);
-    // The kernels stamp DevOutHeader::seq (mapped pinned memory) behind a system-scope fence once a robot's results
-    // are complete: polling it returns a few microseconds before the stream would report the kernel retired.
-    // Stream order still protects everything that follows; a cycle that does not stamp within 20 ms (an error,
-    // or a very large batch) falls back to waiting for the stream.
+    // Every word of a result block (mapped pinned memory) carries the sequence number of the cycle that wrote it:
+    // polling for a complete set returns as soon as the last store has crossed PCIe, microseconds before the stream
+    // would report the kernel retired, with no fence in the kernel.  Stream order still protects everything that
+    // follows; a cycle that is not complete within 20 ms (an error, or a very large batch) falls back to waiting for
+    // the stream.
     bool stamped = false;
     if (h->poll_results) {
       const auto p0 = std::chrono::steady_clock::now();
@@ -1839,15 +1883,16 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
         stamped = true;
         for (int r = 0; r < h->R && stamped; ++r) {
           if (!h->hcyc(r)->run) {continue;}
-          const volatile DevOutHeader * hdr = reinterpret_cast<const volatile DevOutHeader *>(h->h_out + static_cast<size_t>(r) * h->out_stride);
-          stamped = hdr->seq == h->cycle_seq;
+          stamped = results_complete(h, r, h->cycle_seq);
         }
         if (!stamped && (spins & 255u) == 255u &&
           std::chrono::steady_clock::now() - p0 > std::chrono::milliseconds(20)) {break;}
       }
-      std::atomic_thread_fence(std::memory_order_acquire);
     }
     if (!stamped) {CU_CHECK(h, cudaStreamSynchronize(h->stream));}
+    for (int r = 0; r < h->R; ++r) {
+      if (h->hcyc(r)->run) {unpack_results(h, r);}
+    }
     tick(4, tp);
     // A window-only attempt may have missed for SOME robots of a fleet (a lookup outside the uploaded window: that
     // robot committed nothing).  The others are finished now — their results stand, they are not run again — and
@@ -2015,6 +2060,7 @@ int mppi_score_tensors(
     CU_CHECK(h, cudaStreamSynchronize(h->stream));
     CU_CHECK(h, cudaMemcpy(h->d_red + robot * RED_WORDS, init, sizeof(init), cudaMemcpyHostToDevice));
   }
+  unpack_results(h, static_cast<int>(robot));
   const DevOutHeader * hdr = reinterpret_cast<const DevOutHeader *>(h->h_out + h->out_stride * robot);
   if (fail_flag) {*fail_flag = hdr->fail_flag;}
   if (furthest_out) {*furthest_out = hdr->furthest;}
@@ -2488,6 +2534,7 @@ int mppi_shard_end(MppiHandle * h, MppiCycleOut * out)
   for (int r = 0; r < h->R; ++r) {
     bool retry = false;
     out[r].status = MPPI_OK;
+    unpack_results(h, r);
     int rc = finish_attempt(h, r, out[r], retry);
     if (rc != MPPI_OK) {return rc;}
     if (retry) {result = 1;}  // caller re-uploads (mppi_shard_retry) and repeats the phases

@@ -144,7 +144,7 @@ struct DevOutHeader
   float softmax_sum;
   int32_t map_miss;   // a lookup fell outside the uploaded costmap window while the full map was not resident:
                       // nothing was committed (control sequence, filter history); the host uploads the map and reruns
-  uint32_t seq;       // DevCycle::seq of the cycle these results belong to, written LAST behind a system-scope fence
+  uint32_t seq;       // DevCycle::seq of the cycle these results belong to
   int32_t critics_evaluated;  // how many entries of the critic list CriticManager::evalTrajectoriesScores walked before
                               // fail_flag stopped it (critic_manager.cpp:89-93): n_critics if it never did
   int32_t pad[1];
@@ -215,7 +215,7 @@ struct KArgs
   int32_t vis_traj_step, vis_time_step, vis_n_traj, vis_n_pts;
   const uint8_t * win_packets;  // robot r's rows start at DevCycle::win_packet_off
   int32_t map_resident;
-  int32_t stamp_results;   // the host polls DevOutHeader::seq: publish it behind a system-scope fence (costs ~2 us in the kernel)
+  int32_t stamp_results;   // unused since results carry their own tags (kept: part of the plan key)
   const float * path;   // [R][4][max_path]: x, y, yaw, integrated distance
   const uint8_t * path_valid;  // [R][max_path]
   DevCycle * cyc;       // [R]
@@ -227,8 +227,14 @@ struct KArgs
   const float * hist_in;
   const DevStatic * st;
   long long * phase_clocks;  // [R][MPPI_FUSED_MAX_CLUSTER][warps][32] SM clock at each phase boundary of the fused kernel, or null
-  uint8_t * out;        // [R][out_stride]
-  size_t out_stride;
+  // Result blocks in mapped pinned host memory, [R][out_words] 8-byte words: word k holds the 32-bit word k of the plain
+  // layout (DevOutHeader, then the control sequence [3][T], then the optimal trajectory [3][T]) in .x and the
+  // sequence number of the cycle that wrote it (DevCycle::seq) in .y.  The host takes a result once every word carries
+  // the number it waits for, so the kernels need no fence and no ordering between their stores.
+  uint2 * out_tag;
+  size_t out_words;
+  int32_t debug_flags;  // MPPI_B200_DEBUG_FLAGS (measurements only): bit 0 = the fused kernel rehearses its finalize once
+  int32_t pad_debug;
 };
 
 #endif  // NAVIGATION2_B200_CSRC_MPPI_DEVICE_H_
