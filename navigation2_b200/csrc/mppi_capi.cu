@@ -158,6 +158,8 @@ struct MppiHandle
   bool poll_results = true;       // MPPI_B200_NO_POLL=1: wait for the stream instead of polling the result stamp
   uint64_t h2d_bytes = 0;         // bytes of costmaps, cycle blocks and window packets copied host -> device so far
   uint64_t window_misses = 0;     // window-only attempts that had to be repeated with the whole map
+  bool zero_copy = false;         // MPPI_B200_ZERO_COPY=1: single-launch window-only cycles read the cycle block and the window rows
+                                  // straight from the pinned host arena (no cudaMemcpyAsync ahead of the kernel)
   bool window_only = true;        // MPPI_B200_NO_WINDOW_ONLY=1: single-launch cycles upload the whole map (A/B measurements)
   bool window_only_general = true;  // MPPI_B200_NO_WINDOW_GENERAL=1: the general kernels always get whole maps
   uint8_t * h_cycle_block = nullptr;
@@ -503,6 +505,7 @@ int allocate(MppiHandle * h)
   if (const char * e = std::getenv("MPPI_B200_NO_WINDOW_ONLY"); e && e[0] == '1') {h->window_only = false;}
   if (const char * e = std::getenv("MPPI_B200_NO_WINDOW_GENERAL"); e && e[0] == '1') {h->window_only_general = false;}
   if (const char * e = std::getenv("MPPI_B200_NO_POLL"); e && e[0] == '1') {h->poll_results = false;}
+  if (const char * e = std::getenv("MPPI_B200_ZERO_COPY"); e) {h->zero_copy = e[0] == '1';}
   if (const char * e = std::getenv("MPPI_B200_NO_NOISE_PREFETCH"); e && e[0] == '1') {h->noise_prefetch = false;}
   if (const char * e = std::getenv("MPPI_B200_WINDOW_HALF"); e && std::atoi(e) > 0) {h->window_half_override = std::atoi(e);}
   if (const char * e = std::getenv("MPPI_B200_PHASE_CLOCKS"); e && e[0] == '1') {
@@ -1028,11 +1031,19 @@ enum class CycleSource
 
 int enqueue_iterations(
   MppiHandle * h, cudaStream_t stream, const LaunchPlan & plan, bool fresh_costs = false, CycleSource source = CycleSource::LIVE,
-  bool window_only = false)
+  bool window_only = false, bool zero_copy = false)
 {
   KArgs a = make_args(h);
   a.map_resident = window_only ? 0 : 1;
   a.stamp_results = (h->poll_results && source == CycleSource::LIVE) ? 1 : 0;
+  if (zero_copy) {
+    // the kernel's first phase pulls the cycle block, the path arrays and the packed window rows over PCIe from the
+    // pinned host arena (same layout as the device arena; pinned memory is device-accessible at its own address)
+    a.cyc_in = reinterpret_cast<const DevCycle *>(h->h_cycle_block);
+    a.path = reinterpret_cast<const float *>(h->h_cycle_block + sizeof(DevCycle) * h->R);
+    a.path_valid = h->h_cycle_block + sizeof(DevCycle) * h->R + sizeof(float) * 4 * h->max_path * h->R;
+    a.win_packets = h->h_packets;
+  }
   const KArgs live = a;
   const int iters = static_cast<int>(h->cfg.iteration_count);
   // the path arrays never change within a cycle: they are read from the source block by every iteration
@@ -1777,16 +1788,19 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
     const bool window_only = (single_copy || window_general) && h->window_only && !force_resident &&
       h->cfg.iteration_count == 1 && h->packets_capacity > 0 && !any_device_only && host_maps && h->cfg.shard_world == 1;
     h->defer_map_upload = single_copy;
+    const bool zero_copy = window_only && single_copy && h->zero_copy;
     if (window_only) {
       rc = fill_window_packets(h);
-      if (rc == MPPI_OK) {rc = upload_cycle_and_packets(h, h->stream);}
+      if (rc == MPPI_OK && !zero_copy) {rc = upload_cycle_and_packets(h, h->stream);}
+      if (zero_copy) {h->h2d_bytes += h->cycle_block_bytes + h->packets_used;}  // the same bytes cross PCIe, pulled by the kernel
     } else {
       rc = stage_borrowed();
       if (rc == MPPI_OK) {rc = single_copy ? upload_arena(h, h->stream) : wait_map(h, h->stream);}
     }
     if (rc != MPPI_OK) {return rc;}
     if (graphable) {
-      const uint64_t key = plan_key(h, plan) ^ (window_only ? 0x9E3779B97F4A7C15ull : 0ull) ^ (single_copy ? 0x7F4A7C159E3779B9ull : 0ull);
+      const uint64_t key = plan_key(h, plan) ^ (window_only ? 0x9E3779B97F4A7C15ull : 0ull) ^ (single_copy ? 0x7F4A7C159E3779B9ull : 0ull) ^
+        (zero_copy ? 0x3C6EF372FE94F82Bull : 0ull);
       cudaGraphExec_t exec = nullptr;
       for (auto & g : h->graphs) {
         if (g.key == key) {exec = g.exec; break;}
@@ -1809,7 +1823,7 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
         }
         // the finalize kernel writes the result block straight into mapped pinned host memory: no D2H node
         if (crc == MPPI_OK) {
-          crc = enqueue_iterations(h, h->stream, plan, true, CycleSource::LIVE, window_only);
+          crc = enqueue_iterations(h, h->stream, plan, true, CycleSource::LIVE, window_only, zero_copy);
         }
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
