@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mppi_b200.h"
@@ -32,6 +33,20 @@ thread_local std::string g_create_error;
 
 // fleets of at least this many robots share the per-robot host work of a cycle (Optimizer::prepare, window packing,
 // result unpacking) out over the host cores with OpenMP
+// Host threads for the per-robot preparation of a fleet cycle (window packing, prepare_robot): MPPI_B200_HOST_THREADS,
+// else the machine's hardware threads, at most 16.  Given explicitly to every parallel region: launchers such as
+// torchrun export OMP_NUM_THREADS=1, which would silently serialise a fleet's host side.
+static int mppi_host_threads()
+{
+  static const int n = [] {
+      const char * e = std::getenv("MPPI_B200_HOST_THREADS");
+      int v = e ? std::atoi(e) : 0;
+      if (v <= 0) {v = static_cast<int>(std::thread::hardware_concurrency());}
+      return std::max(1, std::min(v, 16));
+    }();
+  return n;
+}
+
 #ifndef MPPI_HOST_PARALLEL_ROBOTS
 #define MPPI_HOST_PARALLEL_ROBOTS 32
 #endif
@@ -1187,7 +1202,7 @@ int fill_window_packets(MppiHandle * h)
   }
   h->packets_used = off;
   // the rows of every robot's window, packed; robots are independent (a fleet's packing is shared out over the host cores)
-#pragma omp parallel for schedule(static) if (h->R >= MPPI_HOST_PARALLEL_ROBOTS)
+#pragma omp parallel for schedule(static) num_threads(mppi_host_threads()) if (h->R >= MPPI_HOST_PARALLEL_ROBOTS)
   for (int r = 0; r < h->R; ++r) {
     const HostRobot & rb = h->robots[r];
     const DevCycle & cy = *h->hcyc(r);
@@ -1739,7 +1754,7 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
   }
   {
     int prc = MPPI_OK;
-#pragma omp parallel for schedule(static) if (h->R >= MPPI_HOST_PARALLEL_ROBOTS)
+#pragma omp parallel for schedule(static) num_threads(mppi_host_threads()) if (h->R >= MPPI_HOST_PARALLEL_ROBOTS)
     for (int r = 0; r < h->R; ++r) {
       out[r].retries = 0;
       out[r].status = MPPI_OK;
