@@ -11,7 +11,9 @@ def load_ncu(path):
     op = gzip.open if path.endswith(".gz") else open
     rows = list(csv.reader(op(path, "rt")))
     hdr = rows[1]
-    return hdr, rows[2:]
+    # an export may hold several launches one after the other: the first one is taken
+    nxt = [i for i, r in enumerate(rows) if i > 1 and r and r[0] == "Kernel Name"]
+    return hdr, rows[2:(nxt[0] if nxt else len(rows))]
 
 def load_lines(path):
     out = []
