@@ -16,3 +16,4 @@ for k,v in sorted(d.items(), key=lambda kv:-sum(kv[1])):
     tail=v[len(v)//2:]
     print(f"{k[:80]:80s} n={len(v):3d} mean_us={sum(v)/len(v)/1e3:8.2f} last-half mean_us={sum(tail)/len(tail)/1e3:8.2f}")
 PY
+for t in 4 8 16; do echo "== C5 fleet, MPPI_B200_HOST_THREADS=$t"; MPPI_B200_HOST_THREADS=$t MPPI_B200_HOST_TIMERS=1 python bench.py --workload c5 --steps 10 --warmup 3 --no-cpu-baseline --no-large-batch 2>&1 | grep -o '"e2e": {[^}]*}\|host timers[^$]*' | cut -c1-400; done
