@@ -1845,7 +1845,11 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
         h->launches = launches_before;  // capture enqueued nothing; launches are counted per replay below
         if (crc != MPPI_OK || ce != cudaSuccess || !graph) {
           if (graph) {cudaGraphDestroy(graph);}
-          cudaGetLastError();
+          const cudaError_t last = cudaGetLastError();
+          // still correct (node-by-node launches, whole maps) but slower, and a launch that cannot be captured is a bug:
+          // say so instead of degrading silently
+          std::fprintf(stderr, "[mppi_b200] warning: capturing the cycle's graph failed (status %d, %s / %s): this handle "
+                       "falls back to node-by-node launches\n", crc, cudaGetErrorString(ce), cudaGetErrorString(last));
           h->use_graphs = false;  // fall back to node-by-node launches for this handle
           continue;
         }
@@ -1853,6 +1857,8 @@ int optimize_impl(MppiHandle * h, const MppiCostmapView * views, const MppiCycle
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) {
           cudaGetLastError();
+          std::fprintf(stderr, "[mppi_b200] warning: instantiating the cycle's graph failed (%s): this handle falls back to "
+                       "node-by-node launches\n", cudaGetErrorString(ce));
           h->use_graphs = false;
           continue;
         }
