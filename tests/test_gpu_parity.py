@@ -422,6 +422,29 @@ def test_window_miss_repeats_the_cycle_with_the_whole_map():
     regular.shutdown(); tiny.shutdown()
 
 
+def test_zero_copy_inputs_match_the_copied_ones():
+    """MPPI_B200_ZERO_COPY=1 (opt-in, measured slower): the single-launch kernel pulls the cycle block, the path
+    arrays and the packed window rows from the pinned host arena itself instead of a cudaMemcpyAsync ahead of it.
+    Same bytes, same kernel: every cycle must end bit-identically, misses included."""
+    regular = _lean_engine()
+    pulled = _lean_engine({"MPPI_B200_ZERO_COPY": "1"})
+    tiny = _lean_engine({"MPPI_B200_ZERO_COPY": "1", "MPPI_B200_WINDOW_HALF": "3"})
+    cells = build_map("blocks", seed=35)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    inp = nb.CycleInput(pose=(10.0, 10.0, 0.0), speed=(0.3, 0.0, 0.0), path=path, goal_checker_xy_tolerance=0.25)
+    for cycle in range(5):
+        a = regular.evalControl(inp, costmaps=(cells, 0.05, 0.0, 0.0))
+        for other in (pulled, tiny):
+            b = other.evalControl(inp, costmaps=(cells, 0.05, 0.0, 0.0))
+            np.testing.assert_array_equal(a.control_sequence, b.control_sequence, err_msg=f"cycle {cycle}")
+            np.testing.assert_array_equal(a.optimal_trajectory, b.optimal_trajectory, err_msg=f"cycle {cycle}")
+            assert a.cmd == b.cmd
+    assert pulled.windowMissCount() == 0 and tiny.windowMissCount() >= 3
+    assert pulled.h2dByteCount() == regular.h2dByteCount()      # the pulled bytes are counted like the copied ones
+    for e in (regular, pulled, tiny):
+        e.shutdown()
+
+
 def test_visualize_on_the_single_launch_path_matches_the_general_kernels():
     """`visualize` (bring-up default, nav2_params.yaml:157): per-critic cost arrays (critic_manager.cpp:79-117),
     collision flags and the strided trajectory samples TrajectoryVisualizer::add draws
