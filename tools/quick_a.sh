@@ -1,3 +1,6 @@
 cd $GRAFT_REPO_ROOT
 export PYTHONPATH=.
-ncu --metrics smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum,smsp__average_warp_latency_per_inst_issued.ratio,sm__inst_executed_pipe_fma.sum,sm__inst_executed_pipe_alu.sum,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fmaheavy.sum,sm__inst_executed_pipe_fmalite.sum --clock-control none -k regex:k_rollout -c 1 --launch-skip 14 python tools/large_batch.py 2 2>&1 | grep -E "k_rollout|smsp__|sm__|gpu__" | cut -c1-150
+for i in 1 2; do python tools/large_batch.py 10 2>&1 | tail -1; done
+python tools/large_batch.py 10 131072 2>&1 | tail -1
+python -m pytest tests/test_gpu_baseline_shapes.py tests/test_gpu_parity.py tests/test_gpu_critics.py -x -q -m gpu 2>&1 | tail -3
+python bench.py --workload c5 --steps 10 --warmup 3 --no-cpu-baseline --no-large-batch 2>/dev/null | grep -o '"ms_per_step": [0-9.]*'
