@@ -622,8 +622,8 @@ def large_batch_roofline(peak, peak_src, stream, flush):
            "frac": achieved / peak, "traffic": measured_traffic("k_rollout_score@2^20x56"),
            "algorithmic_bytes_per_launch": alg, "kernel_ms": ka_ms, "launches_timed": ka_n, "peak_source": peak_src,
            "limiter": "instruction issue and the latency of the per-trajectory serial chain (ncu, profiles/r02_kernels_c4_raw.json: issue "
-                      "slots 69% busy at 116 thread-instructions per trajectory-step, 10.8 cycles per issued instruction, 64 registers, "
-                      "32 of 64 warps resident), not HBM (dram throughput 30%)",
+                      "slots 75% busy at 120 thread-instructions per trajectory-step, 64 registers, 32 of 64 warps resident), not HBM "
+                      "(dram throughput 31%)",
            "kernel_c": {"kernel": "k_softmax_partial", "bound": "hbm", "achieved": achieved_c, "peak": peak, "unit": "GB/s",
                         "frac": achieved_c / peak, "traffic": measured_traffic("k_softmax_partial@2^20x56"),
                         "algorithmic_bytes_per_launch": alg_c, "kernel_ms": kc_ms, "launches_timed": kc_n},
