@@ -57,6 +57,8 @@ _SYMS = {
                                                    C.POINTER(C.c_double), C.c_uint32]),
     "oracle_line_cost": (C.c_double, [_U8, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int]),
     "oracle_compute_cost": (C.c_uint8, [C.c_double] * 4),
+    "oracle_find_path_costs": (C.c_int, [_U8, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_double, _F, _F, C.c_int,
+                                        C.c_int, _U8]),
     "oracle_world_to_map": (C.c_int, [C.c_double] * 5 + [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }
 

@@ -316,29 +316,35 @@ static void setPathFurthestPointIfNotSet(CriticData & data)  // utils.hpp:347-35
 }
 
 // utils.hpp:358-387
-static void findPathCosts(CriticData & data, const Costmap & costmap, bool tracking_unknown)
+static std::vector<bool> pathPointsValid(const Path & path, const Costmap & costmap, bool tracking_unknown)
 {
   unsigned int map_x, map_y;
-  const size_t path_segments_count = data.path.x.size() - 1;
-  data.path_pts_valid = std::vector<bool>(path_segments_count, false);
+  const size_t path_segments_count = path.x.size() - 1;
+  std::vector<bool> path_pts_valid(path_segments_count, false);
   for (unsigned int idx = 0; idx < path_segments_count; idx++) {
-    if (!costmap.worldToMap(data.path.x[idx], data.path.y[idx], map_x, map_y)) {
-      (*data.path_pts_valid)[idx] = false;
+    if (!costmap.worldToMap(path.x[idx], path.y[idx], map_x, map_y)) {
+      path_pts_valid[idx] = false;
       continue;
     }
     switch (costmap.getCost(map_x, map_y)) {
       case (LETHAL_OBSTACLE):
-        (*data.path_pts_valid)[idx] = false;
+        path_pts_valid[idx] = false;
         continue;
       case (INSCRIBED_INFLATED_OBSTACLE):
-        (*data.path_pts_valid)[idx] = false;
+        path_pts_valid[idx] = false;
         continue;
       case (NO_INFORMATION):
-        (*data.path_pts_valid)[idx] = tracking_unknown ? true : false;
+        path_pts_valid[idx] = tracking_unknown ? true : false;
         continue;
     }
-    (*data.path_pts_valid)[idx] = true;
+    path_pts_valid[idx] = true;
   }
+  return path_pts_valid;
+}
+
+static void findPathCosts(CriticData & data, const Costmap & costmap, bool tracking_unknown)
+{
+  data.path_pts_valid = pathPointsValid(data.path, costmap, tracking_unknown);
 }
 
 static void setPathCostsIfNotSet(CriticData & data, const Costmap & costmap, bool tracking_unknown)
@@ -2425,6 +2431,23 @@ int oracle_world_to_map(
   bool ok = cm.worldToMap(wx, wy, a, b);
   *mx = a; *my = b;
   return ok ? 1 : 0;
+}
+
+// utils::findPathCosts (utils.hpp:358-387) on a bare costmap: valid[i] for the n - 1 path segments' first points
+int oracle_find_path_costs(
+  const uint8_t * cells, uint32_t size_x, uint32_t size_y, double resolution, double origin_x, double origin_y,
+  const float * px, const float * py, int n, int tracking_unknown, uint8_t * valid)
+{
+  if (n < 1) {return 0;}
+  oracle::Costmap cm;
+  cm.cells.assign(cells, cells + static_cast<size_t>(size_x) * size_y);
+  cm.size_x = size_x; cm.size_y = size_y; cm.resolution = resolution;
+  cm.origin_x = origin_x; cm.origin_y = origin_y; cm.valid = true;
+  oracle::Path path;
+  path.x.assign(px, px + n); path.y.assign(py, py + n); path.yaws.assign(n, 0.0f);
+  const std::vector<bool> v = oracle::pathPointsValid(path, cm, tracking_unknown != 0);
+  for (size_t i = 0; i < v.size(); ++i) {valid[i] = v[i] ? 1 : 0;}
+  return static_cast<int>(v.size());
 }
 
 }  // extern "C"

@@ -190,6 +190,37 @@ def test_non_shift_mode_controller_period_below_model_dt(batch, full):
         _lean_pair_check(cfg, cells, path, (10.0, 10.0, 0.0), (0.25, 0.0, 0.1), 6, f"non-shift-lean-B{batch}")
 
 
+@pytest.mark.parametrize("model,freq", [("diff_drive", 20.0), ("omni", 30.0)])
+def test_open_loop_uses_the_last_command_not_the_measured_speed(model, freq):
+    """open_loop (optimizer.cpp:300-306; the reference's Omni_openLoopMppiTest, optimizer_unit_tests.cpp:803-877): the
+    rollout starts from the last command instead of the measured twist, which is absurd here on purpose.  The two
+    implementations run free (no resync), so the last command each one carries is its own; shifting (20 Hz) and
+    non-shifting (30 Hz) modes."""
+    cfg = P.nav2_bringup_config(open_loop=True, motion_model=model, controller_frequency=freq)
+    cells = build_map("blocks", seed=4)
+    path = S.arc_path((10.0, 10.0, 0.0), n_points=100)
+    pair = Pair(cfg, cells)
+    x, y, yaw = 10.0, 10.0, 0.0
+    prev = None
+    for i in range(6):
+        inp = nb.CycleInput(pose=(x, y, yaw), speed=(100.0, 100.0 if model == "omni" else 0.0, 100.0), path=path,
+                            goal=tuple(path[-1]), goal_checker_xy_tolerance=0.25)
+        g, c = pair.step(inp)
+        assert_cycle_close(g, c, ctrl_tol=2e-5, label=f"open-loop {model} cycle {i}")
+        assert abs(g.cmd[0]) < 1.0 and abs(g.cmd[2]) < 3.0, "the measured speed of 100 must not enter the rollout"
+        if prev is not None and freq > 20.0:
+            # not shifting: u(0) is acceleration-clamped around the previous command (optimizer.cpp:368-402)
+            period = 1.0 / freq
+            assert abs(g.cmd[0] - prev[0]) <= period * max(cfg.ax_max, -cfg.ax_min) + 1e-6
+            assert abs(g.cmd[2] - prev[2]) <= period * cfg.az_max + 1e-6
+        prev = g.cmd
+        vx, vy, wz = c.cmd
+        x += (vx * np.cos(yaw) - vy * np.sin(yaw)) * cfg.model_dt
+        y += (vx * np.sin(yaw) + vy * np.cos(yaw)) * cfg.model_dt
+        yaw += wz * cfg.model_dt
+    pair.close()
+
+
 @pytest.mark.parametrize("R,batch", [(3, 1000), (20, 2000)])
 def test_fleet_window_miss_reruns_only_the_robots_that_missed(R, batch):
     """Window-only uploads for fleets, single-launch kernel (3 robots) and general kernels (20 robots): with a window

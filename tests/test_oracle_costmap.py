@@ -129,3 +129,37 @@ def test_find_closest_path_pt():
     assert f(5.0) == 4          # beyond the table: last index
     assert f(0.26, 3) == 3      # never moves backwards: the search starts after `init` ...
     assert f(0.36, 3) == 4 and f(0.31, 3) == 3   # ... and compares against vec[init] when init != 0
+
+
+# utils_test.cpp:269-329 findPathCosts: a path point off the costmap (index 1) or on a lethal cell (index 10) is
+# invalid; the point at (4.2, 4.2) maps to cell (42, 42), beside the strip of 253 the fixture writes at row 45, and
+# stays valid like every untouched point
+def test_find_path_costs_reference_fixture():
+    lib = load()
+    cells = np.zeros((50, 50), dtype=np.uint8)           # 5 m x 5 m @ 0.1 m, origin (0, 0)
+    cells[10:31, 10:31] = 254
+    cells[45, 40:46] = 253
+    n = 50
+    px = np.zeros(n, dtype=np.float32)
+    py = np.zeros(n, dtype=np.float32)
+    px[1] = py[1] = 9999999.0                            # off the costmap
+    px[10] = py[10] = 1.5                                # in lethal
+    px[20] = py[20] = 4.2                                # near the inflated strip, on a free cell
+    F = C.POINTER(C.c_float)
+    valid = np.zeros(n, dtype=np.uint8)
+    m = lib.oracle_find_path_costs(cells.ctypes.data_as(U8), 50, 50, 0.1, 0.0, 0.0, px.ctypes.data_as(F),
+                                   py.ctypes.data_as(F), n, 0, valid.ctypes.data_as(U8))
+    assert m == n - 1
+    for i in range(n - 1):
+        assert bool(valid[i]) == (i not in (1, 10)), i
+    # the cases the reference's switch distinguishes (utils.hpp:368-381): inscribed is invalid, unknown follows
+    # track_unknown_space, anything below inscribed is valid
+    px[:] = 0.05
+    py[:] = 0.05
+    for i, c in enumerate([0, 1, 252, 253, 254, 255]):
+        cells[0, i] = c
+        px[i] = 0.1 * i + 0.05
+    for tracking, expect in [(0, [1, 1, 1, 0, 0, 0]), (1, [1, 1, 1, 0, 0, 1])]:
+        lib.oracle_find_path_costs(cells.ctypes.data_as(U8), 50, 50, 0.1, 0.0, 0.0, px.ctypes.data_as(F),
+                                   py.ctypes.data_as(F), n, tracking, valid.ctypes.data_as(U8))
+        assert list(valid[:6]) == expect

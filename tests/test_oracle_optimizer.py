@@ -150,6 +150,25 @@ def test_inter_iteration_constraints_exact_values():
     assert abs(o2.getOptimalControlSequence()[0, 0] - 0.55) < 1e-6    # 0.5 + 0.025 * 2.0
 
 
+# optimizer_unit_tests.cpp:803-877 Omni_openLoopMppiTest: with open_loop the measured robot speed (absurd here) is
+# ignored in favour of the last command, and at 30 Hz (no shifting) every command stays within one controller
+# period of acceleration from the previous one
+def test_omni_open_loop_commands_are_acceleration_bounded():
+    cfg = P.make_config({"controller_frequency": 30.0, "batch_size": 1000, "model_dt": 0.05, "time_steps": 80,
+                         "ax_max": 0.5, "az_max": 0.5, "ay_max": 0.5, "open_loop": True, "motion_model": "omni"})
+    o = OracleOptimizer(cfg)
+    o.setCostmap(np.zeros((50, 50), dtype=np.uint8), 0.1, 0.0, 0.0)
+    period = o.settings()["controller_period"]
+    assert o.settings()["shift_control_sequence"] == 0.0
+    path = np.zeros((17, 3), dtype=np.float64)
+    inp = nb.CycleInput(pose=(999.0, 0.0, 0.0), speed=(100.0, 100.0, 100.0), path=path, goal=(0.0, 0.0, 0.0))
+    c1 = o.evalControl(inp).cmd
+    assert abs(c1[0]) <= period * 0.5 and abs(c1[1]) <= period * 0.5 and abs(c1[2]) <= period * 0.5
+    c2 = o.evalControl(inp).cmd
+    for a, b in zip(c1, c2):
+        assert abs(b - a) <= period * 0.5
+
+
 # optimizer_unit_tests.cpp:377-381 setOffset: controller period > model_dt is a ControllerException
 def test_set_offset_rejects_slow_controller():
     with pytest.raises(Exception):
