@@ -104,3 +104,42 @@ def test_inflation_fails_loudly_without_a_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError):
         inflation.InflationLayer(0.05, 0.22, inflation_radius=0.7)
+
+
+def test_built_kernels_are_sm_100a_and_use_the_instructions_the_design_claims():
+    """The SASS of the in-tree library: sm_100a code; bulk-async staging (UBLKCP) and mbarrier
+    transactions in kernel A; the fused kernel's cluster exchanges as asynchronous remote stores (STAS) with no
+    GPU-wide fence (MEMBAR.ALL.GPU is what every cluster.sync() costs) and one cluster barrier (start-up only);
+    packed FP32 pairs (FADD2 / FMUL2 / FFMA2) in the lean rollout.  Skipped where cuobjdump is not installed."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not installed")
+    lib = os.path.join(ROOT, "navigation2_b200", "libmppi_b200.so")
+    out = subprocess.run([cuobjdump, "-sass", lib], check=True, capture_output=True, text=True).stdout
+    assert "arch = sm_100a" in out
+    kernels, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            kernels[name] = []
+        elif name is not None and "/*" in line:
+            kernels[name].append(line)
+    def body(fragment):
+        found = [k for k in kernels if fragment in k]
+        assert found, f"no kernel named *{fragment}* in the library"
+        return ["\n".join(kernels[k]) for k in found]
+    for sass in body("k_fused_cluster"):
+        assert "STAS" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass
+        assert "MEMBAR.ALL.GPU" not in sass, "a cluster-scope release crept back into the fused kernel"
+        assert sass.count("UCGABAR_ARV") == 1 and sass.count("UCGABAR_WAIT") == 1
+        assert "LDGSTS" in sass
+    for sass in body("k_rollout_lean"):
+        assert "UBLKCP" in sass and "SYNCS.ARRIVE.TRANS64" in sass
+        assert "FFMA2" in sass and "FADD2" in sass and "FMUL2" in sass
+    assert any("UBLKCP" in sass for sass in body("k_rollout_score"))   # the instantiations with the staged noise ring
+    for sass in kernels.values():
+        joined = "\n".join(sass)
+        assert "HMMA" not in joined and "UTCHMMA" not in joined   # nothing on this path is a contraction
