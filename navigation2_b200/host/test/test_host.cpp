@@ -5,6 +5,8 @@
 //   test_host config            parameter parsing / exceptions only (no GPU needed)
 //   test_host run <model> <n>   n closed-loop cycles on the GPU; prints "cmd vx vy wz" per cycle
 //   test_host pathhandler       FeasiblePathHandler mirror, the reference's path_handler.cpp cases (no GPU needed)
+//   test_host visunit           TrajectoryVisualizer mirror, the reference's trajectory_visualizer_tests.cpp cases (no GPU needed)
+//   test_host params            ParametersHandler mirror, the reference's parameter_handler_test.cpp cases (no GPU needed)
 //   test_host visualize <n>     `visualize: true`: CriticsStats + TrajectoryVisualizer output of the last of n cycles (GPU)
 //   test_host fleet <R> <n>     FleetControllerServer: R robots, n cycles, one optimiser call per cycle (GPU)
 //   test_host score             CriticFunction::score on caller tensors (GPU)
@@ -522,12 +524,236 @@ int testInflate()
   return 0;
 }
 
+
+// The reference's trajectory_visualizer_tests.cpp (StateTransition :28-39, VisOptimalTrajectory :41-103,
+// VisCandidateTrajectories :105-137, VisOptimalPath :139-196) against the mirror; the shim's publishers keep the last
+// message instead of delivering it to a subscription.  No GPU needed.
+int testVisualizerUnit()
+{
+  using mppi::TrajectoryVisualizer;
+  std::string name = "test";
+  builtin_interfaces::msg::Time bogus_stamp;
+  {  // StateTransition
+    auto node = std::make_shared<nav2::LifecycleNode>("my_node");
+    mppi::ParametersHandler ph(node, name);
+    TrajectoryVisualizer vis;
+    vis.on_configure(node, "my_name", "map", &ph);
+    vis.on_activate();
+    vis.on_deactivate();
+    vis.on_cleanup();
+  }
+  {  // VisOptimalTrajectory
+    auto node = std::make_shared<nav2::LifecycleNode>("my_node");
+    mppi::ParametersHandler ph(node, name);
+    TrajectoryVisualizer vis;
+    vis.on_configure(node, "my_name", "fkmap", &ph);
+    vis.on_activate();
+    std::vector<std::array<float, 3>> optimal_trajectory;   // empty: nothing to draw
+    vis.add(optimal_trajectory, "Optimal Trajectory", bogus_stamp);
+    vis.visualize();
+    EXPECT(vis.trajectoriesPublisher()->last() == nullptr || vis.trajectoriesPublisher()->last()->markers.empty());
+    optimal_trajectory.assign(20, {1.0f, 1.0f, 1.0f});
+    vis.add(optimal_trajectory, "Optimal Trajectory", bogus_stamp);
+    vis.visualize();
+    const auto * msg = vis.trajectoriesPublisher()->last();
+    EXPECT(msg != nullptr && msg->markers.size() == 20u);   // 20 trajectory points in the given frame
+    EXPECT(msg->markers[0].header.frame_id == "fkmap");
+    EXPECT(msg->markers[0].id == 0 && msg->markers[1].id == 1 && msg->markers[10].id == 10);
+    EXPECT(msg->markers[0].pose.position.x == 1 && msg->markers[0].pose.position.y == 1);
+    EXPECT(msg->markers[0].pose.position.z == 0.06);
+    EXPECT(msg->markers[0].scale.x == 0.03 && msg->markers[0].scale.y == 0.03 && msg->markers[0].scale.z == 0.07);
+    EXPECT(msg->markers[19].scale.x == 0.07 && msg->markers[19].scale.y == 0.07 && msg->markers[19].scale.z == 0.09);
+    for (size_t i = 0; i + 1 != msg->markers.size(); i++) {   // the colour ramp along the trajectory
+      EXPECT(msg->markers[i].color.g < msg->markers[i + 1].color.g);
+      EXPECT(msg->markers[i].color.b < msg->markers[i + 1].color.b);
+      EXPECT(msg->markers[i].color.r == msg->markers[i + 1].color.r);
+      EXPECT(msg->markers[i].color.a == msg->markers[i + 1].color.a);
+    }
+    // marker ids restart with every visualize() (trajectory_visualizer.cpp:204-211 reset)
+    vis.add(optimal_trajectory, "Optimal Trajectory", bogus_stamp);
+    vis.visualize();
+    EXPECT(vis.trajectoriesPublisher()->last()->markers[0].id == 0);
+  }
+  {  // VisCandidateTrajectories: 200 trajectories of 12 points, default strides 5 / 3 -> 40 LINE_STRIP markers of 4 points
+    auto node = std::make_shared<nav2::LifecycleNode>("my_node");
+    mppi::ParametersHandler ph(node, name);
+    TrajectoryVisualizer vis;
+    vis.on_configure(node, "my_name", "fkmap", &ph);
+    vis.on_activate();
+    EXPECT(vis.trajectoryStep() == 5 && vis.timeStep() == 3);
+    const size_t B = 200, T = 12;
+    const size_t n_traj = (B + 4) / 5, n_pts = (T + 2) / 3;
+    std::vector<float> samples(n_traj * n_pts * 2, 1.0f), costs(B);
+    for (size_t i = 0; i < B; ++i) {costs[i] = static_cast<float>(i) / static_cast<float>(B - 1);}   // LinSpaced(200, 0, 1)
+    builtin_interfaces::msg::Time stamp;
+    stamp.sec = 1;
+    vis.add(samples, n_traj, n_pts, costs, {}, stamp);
+    vis.visualize();
+    const auto * msg = vis.trajectoriesPublisher()->last();
+    EXPECT(msg != nullptr && msg->markers.size() == 40u);
+    for (const auto & m : msg->markers) {
+      EXPECT(m.type == visualization_msgs::msg::Marker::LINE_STRIP && m.points.size() == n_pts);
+      EXPECT(m.header.stamp.sec == 1 && m.header.frame_id == "fkmap" && m.ns == "Candidate Trajectories");
+    }
+    // cost -> colour (trajectory_visualizer.cpp:189-202): the cheapest drawn trajectory is green, the costliest red
+    EXPECT(msg->markers.front().color.g == 1.0f && msg->markers.front().color.r == 0.0f);
+    EXPECT(msg->markers.back().color.r == 1.0f && msg->markers.back().color.g < 0.1f);
+    // a colliding trajectory is drawn magenta and does not take part in the normalisation (:121-135, :171-176)
+    std::vector<bool> collisions(B, false);
+    collisions[B - 5] = true;   // the last drawn trajectory (row 195)
+    vis.add(samples, n_traj, n_pts, costs, collisions, stamp);
+    vis.visualize();
+    msg = vis.trajectoriesPublisher()->last();
+    EXPECT(msg->markers.size() == 40u);
+    EXPECT(msg->markers[39].color.r == 1.0f && msg->markers[39].color.g == 0.0f && msg->markers[39].color.b == 1.0f);
+    // nobody listening: nothing is assembled or published (:113-115)
+    const size_t before = vis.trajectoriesPublisher()->publishedCount();
+    vis.trajectoriesPublisher()->setSubscriptionCount(0);
+    vis.add(samples, n_traj, n_pts, costs, {}, stamp);
+    vis.visualize();
+    EXPECT(vis.trajectoriesPublisher()->publishedCount() == before);
+  }
+  {  // VisOptimalPath
+    auto node = std::make_shared<nav2::LifecycleNode>("my_node");
+    mppi::ParametersHandler ph(node, name);
+    builtin_interfaces::msg::Time cmd_stamp;
+    cmd_stamp.sec = 5;
+    cmd_stamp.nanosec = 10;
+    TrajectoryVisualizer vis;
+    vis.on_configure(node, "my_name", "fkmap", &ph);
+    vis.on_activate();
+    std::vector<std::array<float, 3>> optimal_trajectory;
+    vis.add(optimal_trajectory, "Optimal Trajectory", cmd_stamp);
+    vis.visualize();
+    EXPECT(vis.optimalPathPublisher()->last() == nullptr || vis.optimalPathPublisher()->last()->poses.empty());
+    optimal_trajectory.assign(20, {0.0f, 0.0f, 0.0f});
+    for (size_t i = 0; i + 1 != optimal_trajectory.size(); i++) {
+      optimal_trajectory[i] = {static_cast<float>(i), static_cast<float>(i), static_cast<float>(i)};
+    }
+    vis.add(optimal_trajectory, "Optimal Trajectory", cmd_stamp);
+    vis.visualize();
+    const auto * path = vis.optimalPathPublisher()->last();
+    EXPECT(path != nullptr && path->poses.size() == 20u);   // same frame and stamp as the velocity command
+    EXPECT(path->header.frame_id == "fkmap" && path->header.stamp.sec == 5 && path->header.stamp.nanosec == 10u);
+    for (size_t i = 0; i + 1 != path->poses.size(); i++) {
+      EXPECT(path->poses[i].header.frame_id == "fkmap");
+      EXPECT(path->poses[i].pose.position.x == static_cast<float>(i) && path->poses[i].pose.position.y == static_cast<float>(i));
+      EXPECT(path->poses[i].pose.position.z == 0.06);
+      const double yaw = static_cast<double>(optimal_trajectory[i][2]);   // tf2::Quaternion::setRPY(0, 0, yaw)
+      EXPECT(path->poses[i].pose.orientation.x == 0.0 && path->poses[i].pose.orientation.y == 0.0);
+      EXPECT(std::fabs(path->poses[i].pose.orientation.z - std::sin(yaw * 0.5)) < 1e-12);
+      EXPECT(std::fabs(path->poses[i].pose.orientation.w - std::cos(yaw * 0.5)) < 1e-12);
+    }
+  }
+  std::printf("visunit ok\n");
+  return 0;
+}
+
+// The reference's parameter_handler_test.cpp against the mirror: GetSystemParamsTest (:129-151), the static /
+// dynamic split of DynamicAndStaticParametersTest (:153-212: a static parameter rejects the update with a reason, a
+// dynamic one is applied and the post-callbacks run), PrePostDynamicCallbackTest's ordering (:77-127), and updates
+// outside the plugin's namespace left alone (parameters_handler.cpp:66-72).  The mirror applies an accepted update to
+// the node's parameter store and lets the post-callback re-read it (Optimizer::reset in the reference), instead of
+// writing through a reference to the setting.  No GPU needed.
+int testParametersHandler()
+{
+  using mppi::ParameterType;
+  std::string name = "test";
+  {  // GetSystemParamsTest
+    auto node = std::make_shared<nav2::LifecycleNode>("my_node");
+    node->declare_parameter("param1", true);
+    node->declare_parameter(name + ".param2", 7);
+    mppi::ParametersHandler handler(node, name);
+    auto getParameter = handler.getParamGetter("");
+    bool p1 = false;
+    int p2 = 0;
+    getParameter(p1, "param1", false);
+    getParameter(p2, name + ".param2", 0);
+    EXPECT(p1 == true && p2 == 7);
+    auto getParameter2 = handler.getParamGetter(name);
+    p2 = 0;
+    getParameter2(p2, "param2", 0);
+    EXPECT(p2 == 7);
+    // an undeclared parameter is declared with its default (nav2::declare_parameter_if_not_declared)
+    double p3 = 0.0;
+    getParameter2(p3, "param3", 1.5);
+    EXPECT(p3 == 1.5 && node->has_parameter("test.param3"));
+    // numeric settings convert like the reference's static_cast<SettingT>(param_in)
+    float f = 0.0f;
+    unsigned int u = 0;
+    getParameter2(f, "param3", 0.0);
+    getParameter2(u, "param2", 0);
+    EXPECT(f == 1.5f && u == 7u);
+  }
+  {  // DynamicAndStaticParametersTest
+    auto node = std::make_shared<nav2::LifecycleNode>("my_node");
+    node->declare_parameter("test.dynamic_int", 7);
+    node->declare_parameter("test.static_int", 7);
+    mppi::ParametersHandler handler(node, name);
+    handler.start();
+    auto getParameter = handler.getParamGetter("");
+    int p1 = 0, p2 = 0;
+    getParameter(p1, "test.dynamic_int", 0, ParameterType::Dynamic);
+    getParameter(p2, "test.static_int", 0, ParameterType::Static);
+    EXPECT(p1 == 7 && p2 == 7);
+    int post_runs = 0;
+    handler.addPostCallback([&]() {   // what Optimizer::reset does in the mirror: read the settings again
+        ++post_runs;
+        getParameter(p1, "test.dynamic_int", 0, ParameterType::Dynamic);
+        getParameter(p2, "test.static_int", 0, ParameterType::Static);
+      });
+    auto result = handler.setDynamic("test.static_int", 10);
+    EXPECT(!result.successful && !result.reason.empty());
+    EXPECT(result.reason.rfind("Rejected change to static parameter: ", 0) == 0);
+    EXPECT(result.reason.find("test.static_int") != std::string::npos);
+    EXPECT(post_runs == 0 && p2 == 7);
+    result = handler.setDynamic("test.dynamic_int", 10);
+    EXPECT(result.successful && result.reason.empty());
+    EXPECT(post_runs == 1 && p1 == 10 && p2 == 7);   // only the dynamic one changed
+    // not this plugin's parameter: accepted, untouched, no callbacks
+    result = handler.setDynamic("my_node.verbose", true);
+    EXPECT(result.successful && post_runs == 1 && !node->has_parameter("my_node.verbose"));
+  }
+  {  // PrePostDynamicCallbackTest: validation runs before the update, the post-callbacks after it
+    auto node = std::make_shared<nav2::LifecycleNode>("my_node");
+    node->declare_parameter("test.flag", false);
+    mppi::ParametersHandler handler(node, name);
+    bool pre_triggered = false, post_triggered = false, order_ok = true;
+    handler.addPreCallback(
+      "test.flag", [&](const std::string &, const nav2::ParameterValue &, mppi::SetParametersResult &) {
+        if (post_triggered) {order_ok = false;}
+        pre_triggered = true;
+      });
+    handler.addPostCallback([&]() {if (!pre_triggered) {order_ok = false;} post_triggered = true;});
+    auto result = handler.setDynamic("test.flag", true);
+    EXPECT(result.successful && pre_triggered && post_triggered && order_ok);
+    EXPECT(std::get<bool>(node->get_parameter("test.flag")) == true);
+    // a pre-callback that rejects keeps the old value and skips the post-callbacks
+    post_triggered = false;
+    handler.addPreCallback(
+      "test.flag", [&](const std::string &, const nav2::ParameterValue &, mppi::SetParametersResult & r) {
+        r.successful = false;
+        r.reason = "no";
+      });
+    result = handler.setDynamic("test.flag", false);
+    EXPECT(!result.successful && result.reason == "no" && !post_triggered);
+    EXPECT(std::get<bool>(node->get_parameter("test.flag")) == true);
+    // the mutex the control loop shares with the updates (parameters_handler.hpp:100-104) is free again
+    EXPECT(handler.getLock()->try_lock());
+    handler.getLock()->unlock();
+  }
+  std::printf("params ok\n");
+  return 0;
+}
+
 int main(int argc, char ** argv)
 {
   try {
     if (argc >= 2 && std::strcmp(argv[1], "config") == 0) {return testConfig();}
     if (argc >= 2 && std::strcmp(argv[1], "inflate") == 0) {return testInflate();}
     if (argc >= 2 && std::strcmp(argv[1], "pathhandler") == 0) {return testPathHandler();}
+    if (argc >= 2 && std::strcmp(argv[1], "visunit") == 0) {return testVisualizerUnit();}
+    if (argc >= 2 && std::strcmp(argv[1], "params") == 0) {return testParametersHandler();}
     if (argc >= 3 && std::strcmp(argv[1], "visualize") == 0) {return testVisualize(std::atoi(argv[2]));}
     if (argc >= 4 && std::strcmp(argv[1], "fleet") == 0) {return testFleet(std::atoi(argv[2]), std::atoi(argv[3]));}
     if (argc >= 2 && std::strcmp(argv[1], "score") == 0) {return testScore();}

@@ -109,6 +109,25 @@ def test_feasible_path_handler_mirror():
     assert "pathhandler ok" in out.stdout
 
 
+def test_trajectory_visualizer_mirror_reference_cases():
+    """mppi::TrajectoryVisualizer mirror (SURVEY.md section 8f row 1, host half): the four cases of the reference's
+    test/trajectory_visualizer_tests.cpp (state transition, optimal trajectory markers, candidate trajectories at the
+    default strides, optimal path with the command's stamp) plus collision colouring and the no-subscriber early
+    return, no GPU needed."""
+    out = subprocess.run([BIN, "visunit"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "visunit ok" in out.stdout
+
+
+def test_parameters_handler_mirror_reference_cases():
+    """mppi::ParametersHandler mirror: the reference's test/parameter_handler_test.cpp (namespaced getters, static
+    parameters reject dynamic updates with a reason, pre-callbacks run before and post-callbacks after an accepted
+    update, foreign parameters are left alone), no GPU needed."""
+    out = subprocess.run([BIN, "params"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "params ok" in out.stdout
+
+
 def _host_fixture_cfg(**extra):
     from navigation2_b200 import params as P
     p = {"batch_size": 2000, "time_steps": 56, "iteration_count": 1, "motion_model": "diff_drive", "controller_frequency": 20.0}
