@@ -147,6 +147,25 @@ int testConfig()
     try {dd.predict(st);} catch (const nav2_core::ControllerException &) {t2 = true;}
     EXPECT(t2);
   }
+  // critic_manager_test.cpp:130-148 CriticLoadingTest: the "critics" parameter names what is loaded, in order;
+  // :93-128: getFullName
+  {
+    auto node4 = std::make_shared<nav2::LifecycleNode>("my_node");
+    node4->declare_parameter("critic_manager.critics", std::vector<std::string>{"ConstraintCritic", "PreferForwardCritic"});
+    std::string test_name = "test";
+    mppi::ParametersHandler ph4(node4, test_name);
+    mppi::CriticManager cm4;
+    cm4.on_configure(node4, "critic_manager", costmap_ros, &ph4);
+    EXPECT(cm4.critics().size() == 2u);
+    EXPECT(cm4.critics()[0]->params().type == MPPI_CRITIC_CONSTRAINT && cm4.critics()[1]->params().type == MPPI_CRITIC_PREFER_FORWARD);
+    EXPECT(cm4.getFullName("name") == "mppi::critics::name");
+    // no "critics" parameter: nothing is loaded (critic_manager.cpp:47 default {})
+    auto node5 = std::make_shared<nav2::LifecycleNode>("my_node");
+    mppi::ParametersHandler ph5(node5, test_name);
+    mppi::CriticManager cm5;
+    cm5.on_configure(node5, "critic_manager", costmap_ros, &ph5);
+    EXPECT(cm5.critics().empty());
+  }
   EXPECT(std::fabs(tf2::getYaw(tf2::quaternionFromYaw(0.7)) - 0.7) < 1e-12);
   EXPECT(std::fabs(tf2::getYaw(tf2::quaternionFromYaw(-2.9)) + 2.9) < 1e-12);
   std::printf("config ok\n");
