@@ -124,7 +124,12 @@ private:
 };
 
 // ---- motion models (motion_models.xml) ----
-struct ControlSequence {std::vector<float> vx, vy, wz;};
+// models/control_sequence.hpp:37-49
+struct ControlSequence
+{
+  std::vector<float> vx, vy, wz;
+  void reset(unsigned int time_steps) {vx.assign(time_steps, 0.0f); vy.assign(time_steps, 0.0f); wz.assign(time_steps, 0.0f);}
+};
 
 // models::State as the plugin API sees it (models/state.hpp:31-57): B x T column-major float tensors
 namespace models
@@ -136,8 +141,29 @@ struct State
   geometry_msgs::msg::PoseStamped pose;
   geometry_msgs::msg::Twist speed;
   float local_path_length{0.0f};
+  // models/state.hpp:46-56
+  void reset(unsigned int batch, unsigned int steps)
+  {
+    batch_size = batch; time_steps = steps;
+    const size_t n = static_cast<size_t>(batch) * steps;
+    for (auto * v : {&vx, &vy, &wz, &cvx, &cvy, &cwz}) {v->assign(n, 0.0f);}
+  }
 };
-struct Trajectories {std::vector<float> x, y, yaws;};   // models/trajectories.hpp:27-41
+struct Trajectories   // models/trajectories.hpp:27-41
+{
+  std::vector<float> x, y, yaws;
+  void reset(unsigned int batch_size, unsigned int time_steps)
+  {
+    const size_t n = static_cast<size_t>(batch_size) * time_steps;
+    x.assign(n, 0.0f); y.assign(n, 0.0f); yaws.assign(n, 0.0f);
+  }
+};
+struct Path   // models/path.hpp:27-42
+{
+  std::vector<float> x, y, yaws;
+  void reset(unsigned int size) {x.assign(size, 0.0f); y.assign(size, 0.0f); yaws.assign(size, 0.0f);}
+};
+using ControlSequence = mppi::ControlSequence;
 }  // namespace models
 
 class MotionModel

@@ -166,6 +166,27 @@ int testConfig()
     cm5.on_configure(node5, "critic_manager", costmap_ros, &ph5);
     EXPECT(cm5.critics().empty());
   }
+  // models_test.cpp:25-128: reset() zeroes and resizes ControlSequence / Path / State / Trajectories
+  {
+    mppi::models::ControlSequence sequence;
+    sequence.vx.assign(10, 1.0f); sequence.vy.assign(10, 1.0f); sequence.wz.assign(10, 1.0f);
+    sequence.reset(20);
+    EXPECT(sequence.vx[4] == 0 && sequence.vy[4] == 0 && sequence.wz[4] == 0);
+    EXPECT(sequence.vx.size() == 20u && sequence.vy.size() == 20u && sequence.wz.size() == 20u);
+    mppi::models::Path path;
+    path.x.assign(10, 1.0f); path.y.assign(10, 1.0f); path.yaws.assign(10, 1.0f);
+    path.reset(20);
+    EXPECT(path.x[4] == 0 && path.y[4] == 0 && path.yaws[4] == 0 && path.x.size() == 20u && path.yaws.size() == 20u);
+    mppi::models::State state;
+    state.vx.assign(100, 1.0f); state.cwz.assign(100, 1.0f);
+    state.reset(20, 40);
+    EXPECT(state.vx[4] == 0 && state.cwz[4] == 0 && state.batch_size == 20u && state.time_steps == 40u);
+    for (const auto * v : {&state.vx, &state.vy, &state.wz, &state.cvx, &state.cvy, &state.cwz}) {EXPECT(v->size() == 800u);}
+    mppi::models::Trajectories trajectories;
+    trajectories.x.assign(100, 1.0f);
+    trajectories.reset(20, 2);
+    EXPECT(trajectories.x[4] == 0 && trajectories.x.size() == 40u && trajectories.y.size() == 40u && trajectories.yaws.size() == 40u);
+  }
   EXPECT(std::fabs(tf2::getYaw(tf2::quaternionFromYaw(0.7)) - 0.7) < 1e-12);
   EXPECT(std::fabs(tf2::getYaw(tf2::quaternionFromYaw(-2.9)) + 2.9) < 1e-12);
   std::printf("config ok\n");
