@@ -42,7 +42,7 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-METRIC = "MPPI trajectory-steps scored/sec at batch 2000x56; p50 optimize() latency"
+METRIC = "MPPI trajectory-steps scored/sec at batch 2000\u00d756; p50 optimize() latency"   # BASELINE.json's metric, character for character
 UNIT = "trajectory-steps/s"
 
 
