@@ -420,8 +420,48 @@ protected:
 
 }  // namespace mppi
 
+namespace mppi::utils
+{
+// builtin_interfaces::msg::Time + rclcpp::Duration::from_seconds(seconds): the duration truncated to nanoseconds
+inline builtin_interfaces::msg::Time addSeconds(const builtin_interfaces::msg::Time & stamp, double seconds)
+{
+  const int64_t total = static_cast<int64_t>(stamp.sec) * 1000000000LL + static_cast<int64_t>(stamp.nanosec) +
+    static_cast<int64_t>(seconds * 1e9);
+  builtin_interfaces::msg::Time out;
+  int64_t sec = total / 1000000000LL, nsec = total % 1000000000LL;
+  if (nsec < 0) {nsec += 1000000000LL; --sec;}
+  out.sec = static_cast<int32_t>(sec);
+  out.nanosec = static_cast<uint32_t>(nsec);
+  return out;
+}
+
+// utils::toTrajectoryMsg (tools/utils.hpp:174-201): the optimal trajectory (rows of x, y, yaw) with the optimal control
+// sequence's velocities, one point per time step, stamped header.stamp + i * model_dt
+inline std::unique_ptr<nav_msgs::msg::Trajectory> toTrajectoryMsg(
+  const std::vector<std::array<float, 3>> & trajectory, const ControlSequence & control_sequence, const double & model_dt,
+  const std_msgs::msg::Header & header)
+{
+  auto trajectory_msg = std::make_unique<nav_msgs::msg::Trajectory>();
+  trajectory_msg->header = header;
+  trajectory_msg->points.resize(trajectory.size());
+  for (size_t i = 0; i < trajectory.size(); ++i) {
+    auto & curr_pt = trajectory_msg->points[i];
+    curr_pt.header.frame_id = header.frame_id;
+    curr_pt.header.stamp = addSeconds(header.stamp, static_cast<double>(i) * model_dt);
+    curr_pt.pose.position.x = trajectory[i][0];
+    curr_pt.pose.position.y = trajectory[i][1];
+    curr_pt.pose.orientation = tf2::quaternionFromYaw(trajectory[i][2]);
+    curr_pt.velocity.linear.x = control_sequence.vx[i];
+    curr_pt.velocity.angular.z = control_sequence.wz[i];
+    if (!control_sequence.vy.empty()) {curr_pt.velocity.linear.y = control_sequence.vy[i];}
+  }
+  return trajectory_msg;
+}
+}  // namespace mppi::utils
+
 namespace nav2_mppi_controller
 {
+
 // controller.hpp:39-131 — the nav2_core::Controller plugin (pluginlib class "nav2_mppi_controller::MPPIController")
 class MPPIController : public nav2_core::Controller
 {
@@ -443,6 +483,8 @@ public:
   mppi::Optimizer & optimizer() {return optimizer_;}
   const std::vector<std::array<float, 3>> & lastOptimalTrajectory() const {return optimal_trajectory_;}
   mppi::TrajectoryVisualizer & trajectoryVisualizer() {return trajectory_visualizer_;}
+  // "~/optimal_trajectory" (controller.cpp:43-55): exists only with publish_optimal_trajectory
+  nav2::Publisher<nav_msgs::msg::Trajectory> * optimalTrajectoryPublisher() {return opt_traj_pub_.get();}
 
 protected:
   void visualize(const builtin_interfaces::msg::Time & cmd_stamp, const std::vector<std::array<float, 3>> & optimal_trajectory);
@@ -458,6 +500,7 @@ protected:
   bool visualize_{false};
   int critic_index_to_visualize_{0};
   bool publish_optimal_trajectory_{false};
+  std::unique_ptr<nav2::Publisher<nav_msgs::msg::Trajectory>> opt_traj_pub_;
 };
 }  // namespace nav2_mppi_controller
 

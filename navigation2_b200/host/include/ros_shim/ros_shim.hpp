@@ -30,7 +30,13 @@ struct Twist {Vector3 linear; Vector3 angular;};
 struct TwistStamped {std_msgs::msg::Header header; Twist twist;};
 }  // namespace geometry_msgs::msg
 
-namespace nav_msgs::msg {struct Path {std_msgs::msg::Header header; std::vector<geometry_msgs::msg::PoseStamped> poses;};}
+namespace nav_msgs::msg
+{
+struct Path {std_msgs::msg::Header header; std::vector<geometry_msgs::msg::PoseStamped> poses;};
+// nav_msgs/msg/TrajectoryPoint.msg, nav_msgs/msg/Trajectory.msg (what "~/optimal_trajectory" carries)
+struct TrajectoryPoint {std_msgs::msg::Header header; geometry_msgs::msg::Pose pose; geometry_msgs::msg::Twist velocity;};
+struct Trajectory {std_msgs::msg::Header header; std::vector<TrajectoryPoint> points;};
+}  // namespace nav_msgs::msg
 
 namespace std_msgs::msg {struct ColorRGBA {float r{0}, g{0}, b{0}, a{0};};}
 namespace visualization_msgs::msg

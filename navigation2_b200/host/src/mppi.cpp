@@ -849,6 +849,9 @@ void MPPIController::configure(
   getParam(publish_optimal_trajectory_, "publish_optimal_trajectory", false);
   optimizer_.initialize(parent_, name_, costmap_ros_, tf_buffer_, parameters_handler_.get());
   trajectory_visualizer_.on_configure(parent_, name_, costmap_ros_->getGlobalFrameID(), parameters_handler_.get());
+  if (publish_optimal_trajectory_) {
+    opt_traj_pub_ = std::make_unique<nav2::Publisher<nav_msgs::msg::Trajectory>>("~/optimal_trajectory");
+  }
 }
 
 void MPPIController::cleanup()  // controller.cpp:59-67
@@ -856,17 +859,20 @@ void MPPIController::cleanup()  // controller.cpp:59-67
   optimizer_.shutdown();
   trajectory_visualizer_.on_cleanup();
   parameters_handler_.reset();
+  opt_traj_pub_.reset();
 }
 
 void MPPIController::activate()  // controller.cpp:69-78
 {
   trajectory_visualizer_.on_activate();
   parameters_handler_->start();
+  if (opt_traj_pub_) {opt_traj_pub_->on_activate();}
 }
 
 void MPPIController::deactivate()  // controller.cpp:80-87
 {
   trajectory_visualizer_.on_deactivate();
+  if (opt_traj_pub_) {opt_traj_pub_->on_deactivate();}
 }
 
 // controller.cpp:139-158, plus the CriticsStats message CriticManager publishes inside evalTrajectoriesScores
@@ -903,6 +909,13 @@ geometry_msgs::msg::TwistStamped MPPIController::computeVelocityCommands(
   auto [cmd, optimal_trajectory] =
     optimizer_.evalControl(robot_pose, robot_speed, transformed_global_plan, global_goal.pose, goal_checker);
   optimal_trajectory_ = std::move(optimal_trajectory);
+  if (publish_optimal_trajectory_ && opt_traj_pub_ && opt_traj_pub_->get_subscription_count() > 0) {  // controller.cpp:117-129
+    std_msgs::msg::Header trajectory_header;
+    trajectory_header.stamp = cmd.header.stamp;
+    trajectory_header.frame_id = costmap_ros_->getGlobalFrameID();
+    opt_traj_pub_->publish(mppi::utils::toTrajectoryMsg(
+        optimal_trajectory_, optimizer_.getOptimalControlSequence(), optimizer_.getSettings().model_dt, trajectory_header));
+  }
   if (visualize_) {
     visualize(cmd.header.stamp, optimal_trajectory_);
   }

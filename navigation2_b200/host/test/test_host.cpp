@@ -196,6 +196,7 @@ int testConfig()
 int testRun(const std::string & model, int cycles)
 {
   auto node = makeNode(model);
+  node->declare_parameter("FollowPath.publish_optimal_trajectory", true);   // controller.cpp:43-55, 117-129
   auto costmap_ros = makeCostmap(true);
   nav2_mppi_controller::MPPIController controller;
   controller.configure(node, "FollowPath", nullptr, costmap_ros);
@@ -227,6 +228,17 @@ int testRun(const std::string & model, int cycles)
   const auto & seq = controller.optimizer().getOptimalControlSequence();
   EXPECT(seq.vx.size() == 56);
   EXPECT(controller.lastOptimalTrajectory().size() == 56);
+  if (cycles > 0) {
+    // "~/optimal_trajectory": the optimal trajectory with the optimal control sequence's velocities (utils::toTrajectoryMsg)
+    auto * traj_pub = controller.optimalTrajectoryPublisher();
+    EXPECT(traj_pub != nullptr && traj_pub->publishedCount() == static_cast<size_t>(cycles));
+    const auto * tm = traj_pub->last();
+    EXPECT(tm != nullptr && tm->points.size() == 56u);
+    EXPECT(tm->points[5].pose.position.x == static_cast<double>(controller.lastOptimalTrajectory()[5][0]));
+    EXPECT(tm->points[5].pose.position.y == static_cast<double>(controller.lastOptimalTrajectory()[5][1]));
+    EXPECT(tm->points[7].velocity.linear.x == static_cast<double>(seq.vx[7]));
+    EXPECT(tm->points[7].velocity.angular.z == static_cast<double>(seq.wz[7]));
+  }
   controller.setSpeedLimit(50.0, true);
   controller.reset();
   // every trajectory collides: NoValidControl after the retries (optimizer.cpp:281-298)
@@ -684,6 +696,35 @@ int testVisualizerUnit()
       EXPECT(std::fabs(path->poses[i].pose.orientation.z - std::sin(yaw * 0.5)) < 1e-12);
       EXPECT(std::fabs(path->poses[i].pose.orientation.w - std::cos(yaw * 0.5)) < 1e-12);
     }
+  }
+  {  // utils_test.cpp:515-578 toTrajectoryMsgTest
+    std::vector<std::array<float, 3>> trajectory;
+    for (int i = 0; i < 5; ++i) {trajectory.push_back({static_cast<float>(i), static_cast<float>(i), static_cast<float>(i)});}
+    mppi::models::ControlSequence control_sequence;
+    control_sequence.vx.assign(5, 1.0f); control_sequence.wz.assign(5, 1.0f); control_sequence.vy.assign(5, 0.0f);
+    std_msgs::msg::Header header;
+    header.frame_id = "map";
+    header.stamp.sec = 100;
+    auto msg = mppi::utils::toTrajectoryMsg(trajectory, control_sequence, 1.0, header);
+    EXPECT(msg->header.frame_id == "map" && msg->header.stamp.sec == 100 && msg->header.stamp.nanosec == 0u);
+    EXPECT(msg->points.size() == 5u);
+    for (int i = 0; i < 5; ++i) {
+      EXPECT(msg->points[i].pose.position.x == static_cast<double>(i) && msg->points[i].pose.position.y == static_cast<double>(i));
+      EXPECT(msg->points[i].velocity.linear.x == 1.0 && msg->points[i].velocity.linear.y == 0.0);
+      EXPECT(msg->points[i].velocity.angular.z == 1.0);
+      EXPECT(msg->points[i].header.stamp.sec == 100 + i && msg->points[i].header.stamp.nanosec == 0u);
+      EXPECT(msg->points[i].header.frame_id == "map");
+      EXPECT(std::fabs(tf2::getYaw(msg->points[i].pose.orientation) - std::remainder(static_cast<double>(i), 2 * M_PI)) < 1e-9);
+    }
+    // model_dt 0.05 from a stamp with nanoseconds: every point's stamp is the header's plus i * 50 ms
+    header.stamp.nanosec = 980000000u;
+    msg = mppi::utils::toTrajectoryMsg(trajectory, control_sequence, 0.05, header);
+    EXPECT(msg->points[0].header.stamp.sec == 100 && msg->points[0].header.stamp.nanosec == 980000000u);
+    EXPECT(msg->points[1].header.stamp.sec == 101 && msg->points[1].header.stamp.nanosec == 30000000u);
+    // no vy in the control sequence (the reference's size() check): linear.y stays zero
+    control_sequence.vy.clear();
+    msg = mppi::utils::toTrajectoryMsg(trajectory, control_sequence, 0.05, header);
+    EXPECT(msg->points[3].velocity.linear.y == 0.0);
   }
   std::printf("visunit ok\n");
   return 0;
